@@ -1,0 +1,149 @@
+/*
+ * haystack_b200.h -- C ABI of libhaystack_b200.so
+ *
+ * B200 (sm_100a) implementation of the continuous high-D scoring path of singleCellHaystack.
+ * The reference (v1.0.3, pure interpreted R) has NO native interface (no src/, no useDynLib:
+ * NAMESPACE:1-59), so this boundary is created at the three spans of
+ * R/haystack_continuous.R that are replaced by device calls:
+ *
+ *   hs_density            <- R/haystack_continuous.R:168-186  (get_dist_two_sets R/haystack_highD.R:17-24,
+ *                            bandwidth :174, density :175-177, reference distribution Q :179-186)
+ *   hs_dkl_dense          <- R/haystack_continuous.R:202-206  (get_D_KL_continuous_highD :350-363)
+ *   hs_dkl_csr            <- R/haystack_continuous.R:207-212  (extract_row_dgRMatrix_as_sparse R/sparse.R:39-49,
+ *                            get_D_KL_continuous_highD_SPARSE :586-602)
+ *   hs_dkl_perm_dense     <- R/haystack_continuous.R:250-265  (dense randomization loop)
+ *   hs_dkl_perm_csr       <- R/haystack_continuous.R:266-283  (sparse randomization loop)
+ *
+ * Conventions
+ *   - Plain C, POD arguments only.  No R, torch or CUDA types in any signature.
+ *   - Host matrices use R's layout: column-major double.  A dgRMatrix is passed as its three
+ *     slots (@p int32 or int64, @j int32 0-based, @x double).
+ *   - Every function returns 0 on success, non-zero on failure; the message is available from
+ *     hs_last_error(ctx) (or hs_last_error(NULL) when no context exists).  Nothing throws or
+ *     longjmps across this boundary.
+ *   - The caller owns every host buffer for the duration of the call only.  The context owns
+ *     all device memory and streams.  The library draws NO random numbers: permutation indices
+ *     are inputs (the R shim produces them with sample()/sample.int(), so set.seed()
+ *     reproducibility is the host's).
+ *   - One context per process and device (one process per GPU; multi-GPU gene sharding is done
+ *     by the host layer with torch.distributed/NCCL).
+ *   - There is no CPU fallback: every entry point fails with HS_ERR_CUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef HAYSTACK_B200_H
+#define HAYSTACK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_ABI_VERSION 1
+
+enum {
+  HS_OK = 0,
+  HS_ERR_INVALID = 1,   /* bad argument (NULL pointer, negative size, shape mismatch) */
+  HS_ERR_STATE = 2,     /* call order: no density stage resident yet */
+  HS_ERR_CUDA = 3,      /* CUDA runtime error or no usable device */
+  HS_ERR_NOMEM = 4      /* device or host allocation failed */
+};
+
+typedef struct hs_ctx hs_ctx;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int hs_abi_version(void);
+/* Create a context on CUDA device `device` (ordinal as seen by this process). */
+int hs_create(int device, hs_ctx** out);
+void hs_destroy(hs_ctx* ctx);
+const char* hs_last_error(const hs_ctx* ctx);
+/* Run all work of this context on an externally owned CUDA stream (a cudaStream_t passed as
+ * void*; NULL restores the context's own stream).  Used by the host layer so that its timing
+ * events and the library's kernels share one stream. */
+int hs_set_stream(hs_ctx* ctx, void* cuda_stream);
+int hs_synchronize(hs_ctx* ctx);
+
+/* ---- density stage (K1) ---------------------------------------------------------------- */
+/* x: n_cells x n_dims column-major, ALREADY scaled by the caller (scale() stays in R,
+ * R/haystack_continuous.R:139-145).  grid: n_grid x n_dims column-major in the same space.
+ * w_q: n_cells cell weights for Q (weights.advanced.Q, :182) or NULL.
+ * Outputs (each may be NULL): bandwidth_out[1]; q_out[n_grid]; density_out[n_cells*n_grid]
+ * column-major fp64 (info$densities, :331); nearest_out[n_cells] 0-based index of the nearest
+ * grid point (first minimum).
+ * Leaves the density matrix (fp32), Q and the bandwidth resident in the context. */
+int hs_density(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims, const double* grid,
+               int n_grid, const double* w_q, double* bandwidth_out, double* q_out,
+               double* density_out, int32_t* nearest_out);
+
+/* Resident density state, for multi-GPU broadcast by the host layer.  The blob is opaque,
+ * device-resident and position independent: export on the rank that ran hs_density, move it
+ * with any collective, import on the others. */
+int hs_density_blob_bytes(const hs_ctx* ctx, int64_t* bytes_out);
+int hs_density_export_dev(hs_ctx* ctx, void* dev_dst, int64_t bytes);
+int hs_density_import_dev(hs_ctx* ctx, const void* dev_src, int64_t bytes);
+/* Shape of the resident state (0,0 when none). */
+int hs_density_shape(const hs_ctx* ctx, int64_t* n_cells_out, int* n_grid_out);
+
+/* ---- observed D_KL (K2 dense, K3 CSR) --------------------------------------------------- */
+/* expr: n_genes x n_cells column-major double with leading dimension ld (>= n_genes), i.e. an
+ * R matrix (rows = genes).  dkl_out[n_genes]. */
+int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* dkl_out);
+
+/* dgRMatrix slots.  p has n_genes+1 entries (int32 when p_is_64 == 0, else int64); j are
+ * 0-based cell ids (any order within a row; Matrix keeps them ascending); x the values.
+ * Explicit zeros are treated like any other stored value, as the reference does (:272). */
+int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x,
+               int64_t n_genes, double* dkl_out);
+
+/* ---- randomized D_KL (K4) --------------------------------------------------------------- */
+/* Dense form: v[n_cells] is the gene's expression row; perm is n_cells x n_perm column-major,
+ * column r being sample.int(n_cells) (values index_base .. n_cells-1+index_base; R passes
+ * index_base = 1).  out[r] = D_KL of v[perm[, r]]  (sample(x = v) == v[sample.int(length(v))]). */
+int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_perm,
+                      int index_base, double* out);
+
+/* Sparse form, batched over genes so that several genes share a launch.
+ * gene_ptr[n_sel+1]: prefix offsets into val (gene s owns val[gene_ptr[s] .. gene_ptr[s+1])).
+ * ind: for gene s, an nnz_s x n_perm column-major block starting at element
+ * gene_ptr[s]*n_perm; column r is sample(x = n_cells, size = nnz_s) -- distinct cell ids paired
+ * in order with val (:275).  out is n_sel x n_perm column-major (all.D_KL.randomized, :245). */
+int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val,
+                    const int32_t* ind, int n_perm, int index_base, double* out);
+
+/* ---- device-resident variants (inputs already in HBM; used by bench.py and by the
+ *      multi-GPU host layer).  Pointers are device pointers in this process. --------------- */
+/* CSR with int64 row pointers, int32 0-based columns, fp32 values; dkl_dev_out fp64[n_genes]. */
+int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,
+                   int64_t n_genes, double* dkl_dev_out);
+/* gene_ptr_dev int64[n_sel+1], val_dev fp32, ind_dev int32 laid out as in hs_dkl_perm_csr;
+ * out_dev fp64 n_sel x n_perm column-major. */
+int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
+                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base,
+                        double* out_dev);
+/* Dense: expr_dev fp32, n_genes x n_cells column-major with leading dimension ld. */
+int hs_dkl_dense_dev(hs_ctx* ctx, const float* expr_dev, int64_t n_genes, int64_t ld,
+                     double* dkl_dev_out);
+/* v_dev fp32[n_cells]; perm_dev int32 n_cells x n_perm column-major; out_dev fp64[n_perm]. */
+int hs_dkl_perm_dense_dev(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
+                          int index_base, double* out_dev);
+/* Density stage on device-resident inputs (x_dev, grid_dev fp64 column-major; w_q_dev fp64 or
+ * NULL); scalars/vectors come back through host pointers as in hs_density. */
+int hs_density_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims,
+                   const double* grid_dev, int n_grid, const double* w_q_dev,
+                   double* bandwidth_out, double* q_out);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+/* Number of kernels of this library launched on this context since creation. */
+int64_t hs_launch_count(const hs_ctx* ctx);
+/* CUDA-event time (ms) of the dominant kernel family in the most recent call:
+ * slot 0 density kernels, 1 CSR contraction, 2 dense contraction, 3 permutation batch,
+ * 4 host<->device copies.  Returns how many slots were written. */
+int hs_last_timers(hs_ctx* ctx, float* ms_out, int n_slots);
+/* Enable (1) / disable (0) the per-call event timers above (they add two event records per
+ * kernel family; off by default). */
+int hs_enable_timers(hs_ctx* ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HAYSTACK_B200_H */

@@ -1,0 +1,584 @@
+// C ABI of libhaystack_b200.so (declared in include/haystack_b200.h): context management,
+// host<->device staging for the host-pointer entry points, and dispatch to the kernel launchers.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "hs_common.cuh"
+
+static thread_local std::string g_global_err;
+
+int hs_fail(hs_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_global_err = buf;
+  return code;
+}
+
+int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes == 0) bytes = 16;
+  if (b.cap >= bytes) return HS_OK;
+  if (b.p) {
+    // the old block may still be in use by queued work
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    HS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  const size_t want = bytes + bytes / 8 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      b.p = nullptr;
+      return hs_fail(ctx, HS_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    b.cap = bytes;
+  } else {
+    b.cap = want;
+  }
+  return HS_OK;
+}
+
+static void hs_free(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+namespace {
+
+struct ScopedTimer {
+  hs_ctx* c;
+  int slot;
+  bool on;
+  ScopedTimer(hs_ctx* ctx, int s) : c(ctx), slot(s), on(ctx->timers) {
+    if (on) cudaEventRecord(c->ev_a, c->stream);
+  }
+  // call after the work has been queued; synchronises only when timers are enabled
+  void stop() {
+    if (!on) return;
+    cudaEventRecord(c->ev_b, c->stream);
+    cudaEventSynchronize(c->ev_b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+    c->t_ms[slot] = ms;
+    on = false;
+  }
+};
+
+int need_density(hs_ctx* ctx) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  if (ctx->N <= 0 || ctx->G <= 0 || !ctx->D32.p)
+    return hs_fail(ctx, HS_ERR_STATE, "no density stage resident: call hs_density first");
+  return HS_OK;
+}
+
+int set_device(hs_ctx* ctx) {
+  HS_CUDA(ctx, cudaSetDevice(ctx->device));
+  return HS_OK;
+}
+
+size_t env_size(const char* name, size_t dflt) {
+  const char* s = getenv(name);
+  if (!s || !*s) return dflt;
+  const long long v = atoll(s);
+  return v > 0 ? (size_t)v : dflt;
+}
+
+constexpr int64_t kBlobHeader = 256;
+
+struct BlobHeader {
+  uint64_t magic;
+  int64_t N;
+  int32_t G;
+  int32_t ldD;
+  double bw;
+};
+constexpr uint64_t kBlobMagic = 0x48535442323030ull;  // "HSTB200"
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int hs_abi_version(void) { return HS_ABI_VERSION; }
+
+const char* hs_last_error(const hs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_global_err.c_str(); }
+
+int hs_create(int device, hs_ctx** out) {
+  if (!out) return hs_fail(nullptr, HS_ERR_INVALID, "hs_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    return hs_fail(nullptr, HS_ERR_CUDA, "no CUDA device available (%s); libhaystack_b200 has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= count)
+    return hs_fail(nullptr, HS_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return hs_fail(nullptr, HS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return hs_fail(nullptr, HS_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                   device, prop.major, prop.minor);
+  hs_ctx* ctx = new (std::nothrow) hs_ctx();
+  if (!ctx) return hs_fail(nullptr, HS_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  bool ok = cudaSetDevice(device) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreate(&ctx->ev_a) == cudaSuccess && cudaEventCreate(&ctx->ev_b) == cudaSuccess;
+  for (int i = 0; ok && i < 2; ++i)
+    ok = cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    hs_fail(nullptr, HS_ERR_CUDA, "context creation failed: %s", msg);
+    hs_destroy(ctx);
+    return HS_ERR_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  *out = ctx;
+  return HS_OK;
+}
+
+void hs_destroy(hs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  DevBuf* bufs[] = {&ctx->D32, &ctx->Q, &ctx->sq, &ctx->rowmin, &ctx->nearest, &ctx->sel, &ctx->qpart,
+                    &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
+                    &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
+                    &ctx->ptrs, &ctx->dense_in};
+  for (DevBuf* b : bufs) hs_free(*b);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+int hs_set_stream(hs_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return HS_OK;
+}
+
+int hs_synchronize(hs_ctx* ctx) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HS_OK;
+}
+
+int64_t hs_launch_count(const hs_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int hs_enable_timers(hs_ctx* ctx, int on) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  ctx->timers = on != 0;
+  return HS_OK;
+}
+
+int hs_last_timers(hs_ctx* ctx, float* ms_out, int n_slots) {
+  if (!ctx || !ms_out) return 0;
+  const int n = std::min(n_slots, (int)HS_T_COUNT);
+  for (int i = 0; i < n; ++i) ms_out[i] = ctx->t_ms[i];
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// density stage
+// ------------------------------------------------------------------------------------------------
+static int density_common(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* g_dev, int G,
+                          const double* w_dev, double* bandwidth_out, double* q_out, double* density_out,
+                          int32_t* nearest_out) {
+  ScopedTimer tm(ctx, HS_T_DENSITY);
+  HS_TRY(hs_run_density(ctx, x_dev, N, d, g_dev, G, w_dev, density_out != nullptr));
+  tm.stop();
+  cudaStream_t st = ctx->stream;
+  if (q_out) HS_CUDA(ctx, cudaMemcpyAsync(q_out, ctx->Q.p, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+  if (density_out)
+    HS_CUDA(ctx, cudaMemcpyAsync(density_out, ctx->dens64.p, sizeof(double) * (size_t)N * G,
+                                 cudaMemcpyDeviceToHost, st));
+  if (nearest_out)
+    HS_CUDA(ctx, cudaMemcpyAsync(nearest_out, ctx->nearest.p, sizeof(int32_t) * (size_t)N,
+                                 cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (bandwidth_out) *bandwidth_out = ctx->bw;
+  return HS_OK;
+}
+
+static int check_density_args(hs_ctx* ctx, const void* x, int64_t N, int d, const void* grid, int G) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  if (!x || !grid) return hs_fail(ctx, HS_ERR_INVALID, "hs_density: x and grid must not be NULL");
+  if (N <= 0 || d <= 0 || G <= 0)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density: n_cells=%lld n_dims=%d n_grid=%d must be positive",
+                   (long long)N, d, G);
+  if (G > 1024) return hs_fail(ctx, HS_ERR_INVALID, "hs_density: n_grid=%d exceeds the supported maximum of 1024", G);
+  if (N > 2147483647LL)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density: n_cells=%lld exceeds int32 cell ids", (long long)N);
+  return HS_OK;
+}
+
+int hs_density(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims, const double* grid, int n_grid,
+               const double* w_q, double* bandwidth_out, double* q_out, double* density_out,
+               int32_t* nearest_out) {
+  HS_TRY(check_density_args(ctx, x, n_cells, n_dims, grid, n_grid));
+  HS_TRY(set_device(ctx));
+  ctx->N = 0;  // state is invalid until the stage completes
+  HS_TRY(hs_ensure(ctx, ctx->xin, sizeof(double) * (size_t)n_cells * n_dims));
+  HS_TRY(hs_ensure(ctx, ctx->gin, sizeof(double) * (size_t)n_grid * n_dims));
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->xin.p, x, sizeof(double) * (size_t)n_cells * n_dims, cudaMemcpyHostToDevice, st));
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->gin.p, grid, sizeof(double) * (size_t)n_grid * n_dims, cudaMemcpyHostToDevice, st));
+  const double* w_dev = nullptr;
+  if (w_q) {
+    HS_TRY(hs_ensure(ctx, ctx->win, sizeof(double) * (size_t)n_cells));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->win.p, w_q, sizeof(double) * (size_t)n_cells, cudaMemcpyHostToDevice, st));
+    w_dev = (const double*)ctx->win.p;
+  }
+  return density_common(ctx, (const double*)ctx->xin.p, n_cells, n_dims, (const double*)ctx->gin.p, n_grid, w_dev,
+                        bandwidth_out, q_out, density_out, nearest_out);
+}
+
+int hs_density_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims, const double* grid_dev,
+                   int n_grid, const double* w_q_dev, double* bandwidth_out, double* q_out) {
+  HS_TRY(check_density_args(ctx, x_dev, n_cells, n_dims, grid_dev, n_grid));
+  HS_TRY(set_device(ctx));
+  ctx->N = 0;
+  return density_common(ctx, x_dev, n_cells, n_dims, grid_dev, n_grid, w_q_dev, bandwidth_out, q_out, nullptr,
+                        nullptr);
+}
+
+int hs_density_shape(const hs_ctx* ctx, int64_t* n_cells_out, int* n_grid_out) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  if (n_cells_out) *n_cells_out = ctx->N;
+  if (n_grid_out) *n_grid_out = ctx->N > 0 ? ctx->G : 0;
+  return HS_OK;
+}
+
+int hs_density_blob_bytes(const hs_ctx* ctx, int64_t* bytes_out) {
+  if (!ctx || !bytes_out) return hs_fail(nullptr, HS_ERR_INVALID, "null argument");
+  if (ctx->N <= 0) {
+    *bytes_out = 0;
+    return HS_OK;
+  }
+  const int64_t qbytes = ((int64_t)sizeof(double) * ctx->G + 255) / 256 * 256;
+  *bytes_out = kBlobHeader + qbytes + (int64_t)sizeof(float) * ctx->N * ctx->ldD;
+  return HS_OK;
+}
+
+int hs_density_export_dev(hs_ctx* ctx, void* dev_dst, int64_t bytes) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  int64_t need = 0;
+  hs_density_blob_bytes(ctx, &need);
+  if (!dev_dst || bytes < need)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_export_dev: need %lld bytes, got %lld", (long long)need,
+                   (long long)bytes);
+  BlobHeader h;
+  memset(&h, 0, sizeof(h));
+  h.magic = kBlobMagic;
+  h.N = ctx->N;
+  h.G = ctx->G;
+  h.ldD = ctx->ldD;
+  h.bw = ctx->bw;
+  char hdr[kBlobHeader];
+  memset(hdr, 0, sizeof(hdr));
+  memcpy(hdr, &h, sizeof(h));
+  cudaStream_t st = ctx->stream;
+  const int64_t qbytes = ((int64_t)sizeof(double) * ctx->G + 255) / 256 * 256;
+  HS_CUDA(ctx, cudaMemcpyAsync(dev_dst, hdr, kBlobHeader, cudaMemcpyHostToDevice, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));  // hdr is a stack buffer
+  HS_CUDA(ctx, cudaMemcpyAsync((char*)dev_dst + kBlobHeader, ctx->Q.p, sizeof(double) * ctx->G,
+                               cudaMemcpyDeviceToDevice, st));
+  HS_CUDA(ctx, cudaMemcpyAsync((char*)dev_dst + kBlobHeader + qbytes, ctx->D32.p,
+                               sizeof(float) * (size_t)ctx->N * ctx->ldD, cudaMemcpyDeviceToDevice, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
+int hs_density_import_dev(hs_ctx* ctx, const void* dev_src, int64_t bytes) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (!dev_src || bytes < kBlobHeader) return hs_fail(ctx, HS_ERR_INVALID, "hs_density_import_dev: blob too small");
+  cudaStream_t st = ctx->stream;
+  char hdr[kBlobHeader];
+  HS_CUDA(ctx, cudaMemcpyAsync(hdr, dev_src, kBlobHeader, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  BlobHeader h;
+  memcpy(&h, hdr, sizeof(h));
+  if (h.magic != kBlobMagic || h.N <= 0 || h.G <= 0 || h.ldD < h.G)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_import_dev: not a density blob");
+  const int64_t qbytes = ((int64_t)sizeof(double) * h.G + 255) / 256 * 256;
+  const int64_t need = kBlobHeader + qbytes + (int64_t)sizeof(float) * h.N * h.ldD;
+  if (bytes < need)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_import_dev: need %lld bytes, got %lld", (long long)need,
+                   (long long)bytes);
+  ctx->N = 0;
+  HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)h.G + 64));
+  HS_TRY(hs_ensure(ctx, ctx->D32, sizeof(float) * (size_t)h.N * h.ldD));
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->Q.p, (const char*)dev_src + kBlobHeader, sizeof(double) * h.G,
+                               cudaMemcpyDeviceToDevice, st));
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->D32.p, (const char*)dev_src + kBlobHeader + qbytes,
+                               sizeof(float) * (size_t)h.N * h.ldD, cudaMemcpyDeviceToDevice, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  ctx->N = h.N;
+  ctx->G = h.G;
+  ctx->ldD = h.ldD;
+  ctx->bw = h.bw;
+  return HS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// observed D_KL, host pointers
+// ------------------------------------------------------------------------------------------------
+// Generic double-buffered staging loop shared by hs_dkl_csr and hs_dkl_perm_csr.
+//   units        : rows (CSR) or selected genes (perm)
+//   hp[u]        : prefix offsets (values per unit); ids per unit = values * ids_per_value
+struct ChunkPlan {
+  std::vector<int64_t> begin;  // unit index where each chunk starts; last entry = n_units
+};
+
+static ChunkPlan plan_chunks(const std::vector<int64_t>& hp, int64_t ids_per_value, size_t target_ids) {
+  ChunkPlan pl;
+  const int64_t n = (int64_t)hp.size() - 1;
+  int64_t u = 0;
+  pl.begin.push_back(0);
+  while (u < n) {
+    int64_t e = u + 1;
+    while (e < n && (size_t)((hp[e + 1] - hp[u]) * ids_per_value) <= target_ids) ++e;
+    pl.begin.push_back(e);
+    u = e;
+  }
+  return pl;
+}
+
+static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_t* ids, const double* vals,
+                       int64_t ids_per_value, bool perm, int n_perm, int index_base, double* host_out,
+                       int timer_slot) {
+  const int64_t n_units = (int64_t)hp.size() - 1;
+  const int64_t n_out = perm ? n_units * n_perm : n_units;
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)std::max<int64_t>(n_out, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->ptrs, sizeof(int64_t) * (size_t)(n_units + 1)));
+  const size_t target = env_size("HS_STAGE_IDS", (size_t)32 << 20);
+  ChunkPlan pl = plan_chunks(hp, ids_per_value, target);
+  int64_t max_vals = 0;
+  for (size_t k = 0; k + 1 < pl.begin.size(); ++k)
+    max_vals = std::max(max_vals, hp[pl.begin[k + 1]] - hp[pl.begin[k]]);
+  for (int b = 0; b < 2; ++b) {
+    HS_TRY(hs_ensure(ctx, ctx->stage_j[b], sizeof(int32_t) * (size_t)(max_vals * ids_per_value)));
+    HS_TRY(hs_ensure(ctx, ctx->stage_x[b], sizeof(double) * (size_t)max_vals));
+  }
+  HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)max_vals * 2 + 64));
+  float* v32[2] = {(float*)ctx->vals32.p, (float*)ctx->vals32.p + max_vals};
+
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, hp.data(), sizeof(int64_t) * (size_t)(n_units + 1),
+                               cudaMemcpyHostToDevice, st));
+  ScopedTimer tm(ctx, timer_slot);
+  const int64_t base0 = hp[0];
+  for (size_t k = 0; k + 1 < pl.begin.size(); ++k) {
+    const int b = (int)(k & 1);
+    const int64_t u0 = pl.begin[k], u1 = pl.begin[k + 1];
+    const int64_t v0 = hp[u0], nv = hp[u1] - hp[u0];
+    if (k >= 2) HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[b], 0));
+    if (nv > 0) {
+      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_j[b].p, ids + (v0 - base0) * ids_per_value,
+                                   sizeof(int32_t) * (size_t)(nv * ids_per_value), cudaMemcpyHostToDevice, cs));
+      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[b].p, vals + (v0 - base0), sizeof(double) * (size_t)nv,
+                                   cudaMemcpyHostToDevice, cs));
+    }
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], cs));
+    HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[b], 0));
+    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, v32[b], nv));
+    // kernels index with the absolute offsets in ptrs[]: shift the chunk bases accordingly
+    const int32_t* ids_dev = (const int32_t*)ctx->stage_j[b].p - v0 * ids_per_value;
+    const float* val_dev = v32[b] - v0;
+    const int64_t* ptr_dev = (const int64_t*)ctx->ptrs.p + u0;
+    if (perm) {
+      HS_TRY(hs_run_perm_csr(ctx, ptr_dev, u1 - u0, val_dev, ids_dev, n_perm, index_base,
+                             (double*)ctx->out.p + u0));
+    } else {
+      HS_TRY(hs_run_csr(ctx, ptr_dev, ids_dev, val_dev, u1 - u0, (double*)ctx->out.p + u0));
+    }
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+  }
+  tm.stop();
+  if (n_out > 0)
+    HS_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->out.p, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
+int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
+               double* dkl_out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || !p || !dkl_out) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: bad arguments");
+  if (n_genes == 0) return HS_OK;
+  std::vector<int64_t> hp((size_t)n_genes + 1);
+  for (int64_t i = 0; i <= n_genes; ++i)
+    hp[i] = p_is_64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
+  for (int64_t i = 0; i < n_genes; ++i)
+    if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: row pointers must be non-decreasing");
+  if (hp[n_genes] > hp[0] && (!j || !x)) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: j/x are NULL");
+  // j and x are addressed from element hp[0] of the caller's slots
+  return staged_rows(ctx, hp, j + hp[0], x + hp[0], 1, false, 1, 0, dkl_out, HS_T_CSR);
+}
+
+int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, const int32_t* ind,
+                    int n_perm, int index_base, double* out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_sel < 0 || n_perm <= 0 || !gene_ptr || !out)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: bad arguments");
+  if (n_sel == 0) return HS_OK;
+  std::vector<int64_t> hp(gene_ptr, gene_ptr + n_sel + 1);
+  if (hp[0] != 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: gene_ptr[0] must be 0");
+  for (int64_t i = 0; i < n_sel; ++i)
+    if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: gene_ptr must be non-decreasing");
+  if (hp[n_sel] > 0 && (!val || !ind)) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: val/ind are NULL");
+  // The kernel writes out[s + r * n_sel_chunk]; run chunk-local column-major blocks into ctx->out and
+  // let staged_rows copy back.  To keep the global layout n_sel x n_perm column-major we need one chunk
+  // or a re-layout; do the re-layout on the host for multi-chunk runs.
+  std::vector<double> tmp;
+  const size_t target = env_size("HS_STAGE_IDS", (size_t)32 << 20);
+  ChunkPlan pl = plan_chunks(hp, n_perm, target);
+  if (pl.begin.size() == 2) return staged_rows(ctx, hp, ind, val, n_perm, true, n_perm, index_base, out, HS_T_PERM);
+  // multi-chunk: run each chunk as its own call (each produces a chunk-local column-major block)
+  for (size_t k = 0; k + 1 < pl.begin.size(); ++k) {
+    const int64_t u0 = pl.begin[k], u1 = pl.begin[k + 1];
+    std::vector<int64_t> sub(hp.begin() + u0, hp.begin() + u1 + 1);
+    const int64_t off = sub[0];
+    for (auto& v : sub) v -= off;
+    tmp.assign((size_t)(u1 - u0) * n_perm, 0.0);
+    HS_TRY(staged_rows(ctx, sub, ind + off * n_perm, val + off, n_perm, true, n_perm, index_base, tmp.data(),
+                       HS_T_PERM));
+    for (int r = 0; r < n_perm; ++r)
+      for (int64_t s = 0; s < u1 - u0; ++s) out[(u0 + s) + (int64_t)r * n_sel] = tmp[(size_t)s + (size_t)r * (u1 - u0)];
+  }
+  return HS_OK;
+}
+
+int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* dkl_out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || ld < n_genes || !dkl_out || (n_genes > 0 && !expr))
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_dense: bad arguments");
+  if (n_genes == 0) return HS_OK;
+  const int64_t N = ctx->N;
+  HS_TRY(hs_ensure(ctx, ctx->dense_in, sizeof(double) * (size_t)n_genes * N));
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)n_genes));
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemcpy2DAsync(ctx->dense_in.p, sizeof(double) * n_genes, expr, sizeof(double) * ld,
+                                 sizeof(double) * n_genes, (size_t)N, cudaMemcpyHostToDevice, st));
+  ScopedTimer tm(ctx, HS_T_DENSE);
+  HS_TRY(hs_run_dense_f64(ctx, (const double*)ctx->dense_in.p, n_genes, n_genes, (double*)ctx->out.p));
+  tm.stop();
+  HS_CUDA(ctx, cudaMemcpyAsync(dkl_out, ctx->out.p, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
+int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_perm, int index_base, double* out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (!v || !perm || !out || n_perm <= 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense: bad arguments");
+  const int64_t N = ctx->N;
+  HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->stage_j[0], sizeof(int32_t) * (size_t)N * n_perm));
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)n_perm));
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, v, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_j[0].p, perm, sizeof(int32_t) * (size_t)N * n_perm,
+                               cudaMemcpyHostToDevice, st));
+  HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p, N));
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_dense(ctx, (const float*)ctx->vals32.p, (const int32_t*)ctx->stage_j[0].p, n_perm,
+                           index_base, (double*)ctx->out.p));
+  tm.stop();
+  HS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, sizeof(double) * (size_t)n_perm, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident variants
+// ------------------------------------------------------------------------------------------------
+int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev, int64_t n_genes,
+                   double* dkl_dev_out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || !p_dev || !dkl_dev_out) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr_dev: bad arguments");
+  ScopedTimer tm(ctx, HS_T_CSR);
+  HS_TRY(hs_run_csr(ctx, p_dev, j_dev, x_dev, n_genes, dkl_dev_out));
+  tm.stop();
+  return HS_OK;
+}
+
+int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
+                        const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_sel < 0 || n_perm <= 0 || !gene_ptr_dev || !out_dev)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_dev: bad arguments");
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_csr(ctx, gene_ptr_dev, n_sel, val_dev, ind_dev, n_perm, index_base, out_dev));
+  tm.stop();
+  return HS_OK;
+}
+
+int hs_dkl_dense_dev(hs_ctx* ctx, const float* expr_dev, int64_t n_genes, int64_t ld, double* dkl_dev_out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || ld < n_genes || !expr_dev || !dkl_dev_out)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_dense_dev: bad arguments");
+  ScopedTimer tm(ctx, HS_T_DENSE);
+  HS_TRY(hs_run_dense_f32(ctx, expr_dev, n_genes, ld, dkl_dev_out));
+  tm.stop();
+  return HS_OK;
+}
+
+int hs_dkl_perm_dense_dev(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm, int index_base,
+                          double* out_dev) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (!v_dev || !perm_dev || !out_dev || n_perm <= 0)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense_dev: bad arguments");
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_dense(ctx, v_dev, perm_dev, n_perm, index_base, out_dev));
+  tm.stop();
+  return HS_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,145 @@
+// Shared definitions for libhaystack_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/haystack_b200.h"
+
+#define HS_PSEUDO 1e-300  // R/haystack_continuous.R:184
+
+// Slots of hs_last_timers
+enum { HS_T_DENSITY = 0, HS_T_CSR = 1, HS_T_DENSE = 2, HS_T_PERM = 3, HS_T_COPY = 4, HS_T_COUNT = 5 };
+
+template <typename T>
+__host__ __device__ __forceinline__ T hs_min(T a, T b) { return a < b ? a : b; }
+template <typename T>
+__host__ __device__ __forceinline__ T hs_max(T a, T b) { return a > b ? a : b; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct hs_ctx {
+  int device = 0;
+  int sm_count = 148;
+  size_t smem_optin = 0;
+  cudaStream_t own_stream = nullptr;   // created by hs_create
+  cudaStream_t stream = nullptr;       // stream all kernels run on (own_stream or external)
+  cudaStream_t copy_stream = nullptr;  // H2D staging for the host-pointer entry points
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // timers
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr}; // staging buffer k has landed
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};  // compute on staging buffer k finished
+  std::string err;
+  int64_t launches = 0;
+  bool timers = false;
+  float t_ms[HS_T_COUNT] = {0, 0, 0, 0, 0};
+
+  // ---- resident density state (written by the density stage) ----
+  int64_t N = 0;   // cells
+  int G = 0;       // grid points
+  int ldD = 0;     // row stride (floats) of D32, multiple of 4
+  double bw = 0.0;
+  DevBuf D32;      // [N][ldD] fp32, cell-major
+  DevBuf Q;        // [G] fp64 normalised reference distribution
+
+  // ---- scratch (grow-only) ----
+  DevBuf sq;        // [G][N] fp64 squared distances
+  DevBuf rowmin;    // [N] fp64
+  DevBuf nearest;   // [N] int32
+  DevBuf sel;       // radix-select state + histograms
+  DevBuf qpart;     // [blocks][G] fp64
+  DevBuf dens64;    // [G][N] fp64 (only when density_out requested)
+  DevBuf xin, gin, win;        // uploaded x / grid / w_q
+  DevBuf part;      // [ksplit][rows][ldP] fp64 partial P
+  DevBuf out;       // fp64 results
+  DevBuf stage_j[2], stage_x[2];  // H2D staging (int32 ids, fp64 values)
+  DevBuf vals32;    // fp32 values
+  DevBuf ptrs;      // int64 row pointers
+  DevBuf dense_in;  // uploaded dense expression (fp64 col-major)
+  void* pinned = nullptr;      // small pinned host bounce buffer
+  size_t pinned_cap = 0;
+};
+
+// ---- error helpers (host) -----------------------------------------------------------------
+int hs_fail(hs_ctx* ctx, int code, const char* fmt, ...);
+int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes);
+
+#define HS_CUDA(ctx, expr)                                                                  \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return hs_fail((ctx), HS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                     __FILE__, __LINE__);                                                   \
+  } while (0)
+
+#define HS_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != HS_OK) return _rc; \
+  } while (0)
+
+#define HS_LAUNCH_CHECK(ctx)                                                                \
+  do {                                                                                      \
+    (ctx)->launches++;                                                                      \
+    cudaError_t _e = cudaGetLastError();                                                    \
+    if (_e != cudaSuccess)                                                                  \
+      return hs_fail((ctx), HS_ERR_CUDA, "kernel launch failed: %s (%s:%d)",                \
+                     cudaGetErrorString(_e), __FILE__, __LINE__);                           \
+  } while (0)
+
+// ---- launchers implemented in the kernel translation units --------------------------------
+// density stage (hs_density.cu): inputs device-resident fp64 column-major
+int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
+                   const double* wq_dev, bool want_dens64);
+// contraction kernels (hs_contract.cu)
+int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,
+               int64_t n_rows, double* out_dev);
+int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
+                    const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
+int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
+int hs_run_dense_f64(hs_ctx* ctx, const double* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
+int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
+                      int index_base, double* out_dev);
+int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n);
+
+#ifdef __CUDACC__
+// ---- device helpers -----------------------------------------------------------------------
+__device__ __forceinline__ double hs_warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Fused KL epilogue for one gene held by one warp (R/haystack_continuous.R:358-360, :597-599).
+// Lane l holds the raw column sums P[l + 32*a], a < NACC; columns >= G are ignored.
+// Returns D_KL on every lane.  All arithmetic fp64, same operation order as the reference:
+// P + pseudo; P / sum(P); sum(P * log(P / Q)).
+template <int NACC>
+__device__ __forceinline__ double hs_kl_epilogue(double (&p)[NACC], const double* __restrict__ Q, int G,
+                                                 int lane) {
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const int j = lane + 32 * a;
+    if (j < G) {
+      p[a] += HS_PSEUDO;
+      s += p[a];
+    }
+  }
+  s = hs_warp_sum(s);
+  double kl = 0.0;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const int j = lane + 32 * a;
+    if (j < G) {
+      const double pn = p[a] / s;
+      kl += pn * log(pn / Q[j]);
+    }
+  }
+  return hs_warp_sum(kl);
+}
+#endif  // __CUDACC__

@@ -1,0 +1,328 @@
+// K2/K3/K4: gene x grid contraction with the fused Kullback-Leibler epilogue.
+//   P     = colSums(D * w)              R/haystack_continuous.R:357   (dense row w)
+//   P     = colSums(D[ind,] * val)      R/haystack_continuous.R:596   (sparse row)
+//   D_KL  = sum(Pn * log(Pn / Q)), Pn = (P + 1e-300) / sum(P + 1e-300)   :358-360, :597-599
+// Accumulation is two-level: fp32 FMAs over a short run of cells, flushed into fp64 running
+// sums, so that the error of a 1e5-term column sum stays ~1e-8 relative (D_KL of weakly
+// structured genes is ~ 1/2 sum (P-Q)^2/Q and amplifies column-sum error ~30x).  The epilogue
+// is fp64 and never writes P to HBM.
+#include <math.h>
+
+#include "hs_common.cuh"
+
+namespace {
+
+// =================================================================================================
+// K3 / K4-sparse: one warp per row; lanes span grid columns; D rows gathered through L2.
+// =================================================================================================
+// PERM == false: CSR. row r owns cols[p[r] .. p[r+1]) and vals at the same offsets.
+// PERM == true : row = s * n_perm + r; gene s owns vals[gp[s] .. gp[s+1]) (nnz_s values) and the
+//                index block starting at cols[gp[s] * n_perm], column r of an nnz_s x n_perm
+//                column-major matrix (R/haystack_continuous.R:275); output is n_sel x n_perm
+//                column-major: out[s + r * n_sel].
+template <int NACC, bool PERM>
+__global__ void __launch_bounds__(256)
+k_rows_gather_kl(const int64_t* __restrict__ ptr, const int32_t* __restrict__ cols,
+                 const float* __restrict__ vals, int64_t n_rows, int n_perm, int64_t n_sel, int col_base,
+                 const float* __restrict__ D, int ldD, int G, int64_t n_cells, const double* __restrict__ Q,
+                 double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int32_t* rc;
+    const float* rv;
+    int64_t nnz;
+    int64_t out_idx;
+    if (PERM) {
+      const int64_t s = row / n_perm;
+      const int r = (int)(row - s * n_perm);
+      const int64_t g0 = ptr[s];
+      nnz = ptr[s + 1] - g0;
+      rc = cols + g0 * n_perm + (int64_t)r * nnz;
+      rv = vals + g0;
+      out_idx = s + (int64_t)r * n_sel;
+    } else {
+      const int64_t g0 = ptr[row];
+      nnz = ptr[row + 1] - g0;
+      rc = cols + g0;
+      rv = vals + g0;
+      out_idx = row;
+    }
+    double acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    for (int64_t base = 0; base < nnz; base += 32) {
+      const int cnt = (int)hs_min<int64_t>(32, nnz - base);
+      int myc = 0;
+      float myv = 0.f;
+      if (lane < cnt) {
+        myc = rc[base + lane] - col_base;
+        myv = rv[base + lane];
+        // ids outside [0, n_cells) cannot be dereferenced: poison the result instead
+        if (myc < 0 || (int64_t)myc >= n_cells) {
+          myc = 0;
+          myv = __int_as_float(0x7fc00000);
+        }
+      }
+      float part[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) part[a] = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const int c = __shfl_sync(0xffffffffu, myc, t);
+        const float v = __shfl_sync(0xffffffffu, myv, t);
+        const float* drow = D + (int64_t)c * ldD;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          const int j = lane + 32 * a;
+          const float dv = (j < G) ? __ldg(drow + j) : 0.f;
+          part[a] = fmaf(v, dv, part[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] += (double)part[a];
+    }
+    const double kl = hs_kl_epilogue<NACC>(acc, Q, G, lane);
+    if (lane == 0) out[out_idx] = kl;
+  }
+}
+
+// =================================================================================================
+// K2 / K4-dense: register-tiled fp32 contraction over cells with split-K partials in fp64.
+// A(row, cell): dense  -> E[row + cell * ld]                       (R matrix, genes x cells)
+//               perm   -> v[perm[cell + row * N] - base]           (sample(x = v), :259)
+// Tile: 64 rows x 128 grid columns per block, 16 cells per stage, 256 threads each owning
+// 4 rows x 8 columns.
+// =================================================================================================
+constexpr int kTM = 64, kTN = 128, kTK = 16, kFlush = 16;  // flush fp32 -> fp64 every 16 stages (256 cells)
+
+template <typename TE, bool PERM>
+__global__ void __launch_bounds__(256)
+k_dense_partial(const TE* __restrict__ E, int64_t ld, const float* __restrict__ v,
+                const int32_t* __restrict__ perm, int index_base, int64_t n_rows, int64_t N,
+                const float* __restrict__ D, int ldD, int G, int cells_per_split, int ldP,
+                double* __restrict__ part) {
+  __shared__ __align__(16) float As[kTK][kTM + 4];
+  __shared__ __align__(16) float Bs[kTK][kTN];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int64_t r0 = (int64_t)blockIdx.x * kTM;
+  const int j0 = blockIdx.z * kTN;
+  const int64_t c_begin = (int64_t)blockIdx.y * cells_per_split;
+  const int64_t c_end = hs_min<int64_t>(N, c_begin + cells_per_split);
+
+  double acc[4][8];
+  float cur[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[i][j] = 0.0;
+      cur[i][j] = 0.f;
+    }
+
+  int stage = 0;
+  for (int64_t c0 = c_begin; c0 < c_end; c0 += kTK, ++stage) {
+    // ---- stage A tile (16 cells x 64 rows) ----
+    if (!PERM) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + 256 * i;       // 0..1023
+        const int kk = e >> 6, rr = e & 63;  // consecutive threads -> consecutive genes (coalesced)
+        const int64_t cell = c0 + kk, row = r0 + rr;
+        float a = 0.f;
+        if (cell < c_end && row < n_rows) a = (float)E[row + cell * ld];
+        As[kk][rr] = a;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int e = tid + 256 * i;
+        const int rr = e >> 4, kk = e & 15;  // consecutive threads -> consecutive cells of one permutation
+        const int64_t cell = c0 + kk, row = r0 + rr;
+        float a = 0.f;
+        if (cell < c_end && row < n_rows) {
+          const int64_t src = (int64_t)perm[cell + row * N] - index_base;
+          a = (src >= 0 && src < N) ? v[src] : __int_as_float(0x7fc00000);
+        }
+        As[kk][rr] = a;
+      }
+    }
+    // ---- stage B tile (16 cells x 128 columns of D) ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = tid + 256 * i;         // 0..2047
+      const int kk = e >> 7, jj = e & 127;
+      const int64_t cell = c0 + kk;
+      const int j = j0 + jj;
+      Bs[kk][jj] = (cell < c_end && j < G) ? D[cell * ldD + j] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kTK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[i][j] = fmaf(a[i], b[j], cur[i][j]);
+    }
+    __syncthreads();
+    if ((stage % kFlush) == kFlush - 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[i][j] += (double)cur[i][j];
+          cur[i][j] = 0.f;
+        }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t row = r0 + ty * 4 + i;
+    if (row >= n_rows) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = j0 + tx + 16 * j;
+      if (col < ldP) part[((int64_t)blockIdx.y * n_rows + row) * ldP + col] = acc[i][j] + (double)cur[i][j];
+    }
+  }
+}
+
+// Sum split-K partials in fixed order and apply the KL epilogue; one warp per row.
+template <int NACC>
+__global__ void __launch_bounds__(256)
+k_rows_epilogue(const double* __restrict__ part, int n_split, int64_t n_rows, int ldP, int G,
+                const double* __restrict__ Q, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  double p[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) p[a] = 0.0;
+  for (int s = 0; s < n_split; ++s) {
+    const double* pr = part + ((int64_t)s * n_rows + row) * ldP;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int j = lane + 32 * a;
+      if (j < G) p[a] += pr[j];
+    }
+  }
+  const double kl = hs_kl_epilogue<NACC>(p, Q, G, lane);
+  if (lane == 0) out[row] = kl;
+}
+
+template <bool PERM>
+int launch_rows_gather(hs_ctx* ctx, const int64_t* ptr, const int32_t* cols, const float* vals,
+                       int64_t n_rows, int n_perm, int64_t n_sel, int col_base, double* out) {
+  if (n_rows <= 0) return HS_OK;
+  const int G = ctx->G;
+  const int nacc = (G + 31) / 32;
+  const int64_t want_blocks = (n_rows + 7) / 8;  // 8 warps per block
+  const int blocks = (int)hs_min<int64_t>(want_blocks, (int64_t)ctx->sm_count * 8);
+  const float* D = (const float*)ctx->D32.p;
+  const double* Q = (const double*)ctx->Q.p;
+#define HS_GATHER_CASE(NA)                                                                          \
+  case NA:                                                                                          \
+    k_rows_gather_kl<NA, PERM><<<blocks, 256, 0, ctx->stream>>>(ptr, cols, vals, n_rows, n_perm, n_sel, \
+                                                                col_base, D, ctx->ldD, G, ctx->N, Q, out); \
+    break;
+  switch (nacc) {
+    HS_GATHER_CASE(1)
+    HS_GATHER_CASE(2)
+    HS_GATHER_CASE(3)
+    HS_GATHER_CASE(4)
+    HS_GATHER_CASE(5)
+    HS_GATHER_CASE(6)
+    HS_GATHER_CASE(7)
+    HS_GATHER_CASE(8)
+    default:
+      if (nacc <= 16) {
+        k_rows_gather_kl<16, PERM><<<blocks, 256, 0, ctx->stream>>>(ptr, cols, vals, n_rows, n_perm, n_sel,
+                                                                    col_base, D, ctx->ldD, G, ctx->N, Q, out);
+      } else if (nacc <= 32) {
+        k_rows_gather_kl<32, PERM><<<blocks, 256, 0, ctx->stream>>>(ptr, cols, vals, n_rows, n_perm, n_sel,
+                                                                    col_base, D, ctx->ldD, G, ctx->N, Q, out);
+      } else {
+        return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d exceeds the supported maximum of 1024", G);
+      }
+  }
+#undef HS_GATHER_CASE
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
+
+int launch_rows_epilogue(hs_ctx* ctx, const double* part, int n_split, int64_t n_rows, int ldP, double* out) {
+  const int G = ctx->G;
+  const int nacc = (G + 31) / 32;
+  const int blocks = (int)((n_rows + 7) / 8);
+  const double* Q = (const double*)ctx->Q.p;
+#define HS_EPI_CASE(NA)                                                                               \
+  k_rows_epilogue<NA><<<blocks, 256, 0, ctx->stream>>>(part, n_split, n_rows, ldP, G, Q, out)
+  if (nacc <= 1) HS_EPI_CASE(1);
+  else if (nacc <= 2) HS_EPI_CASE(2);
+  else if (nacc <= 3) HS_EPI_CASE(3);
+  else if (nacc <= 4) HS_EPI_CASE(4);
+  else if (nacc <= 8) HS_EPI_CASE(8);
+  else if (nacc <= 16) HS_EPI_CASE(16);
+  else if (nacc <= 32) HS_EPI_CASE(32);
+  else return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d exceeds the supported maximum of 1024", G);
+#undef HS_EPI_CASE
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
+
+template <typename TE, bool PERM>
+int launch_dense(hs_ctx* ctx, const TE* E, int64_t ld, const float* v, const int32_t* perm, int index_base,
+                 int64_t n_rows, double* out) {
+  if (n_rows <= 0) return HS_OK;
+  const int G = ctx->G;
+  const int64_t N = ctx->N;
+  const int ldP = (G + 3) & ~3;
+  const int row_tiles = (int)((n_rows + kTM - 1) / kTM);
+  const int col_tiles = (G + kTN - 1) / kTN;
+  // split the cell axis until the launch fills ~2 waves; every split covers a multiple of 256 cells
+  int64_t max_split = (N + 255) / 256;
+  int64_t want = ((int64_t)ctx->sm_count * 2 + (int64_t)row_tiles * col_tiles - 1) / ((int64_t)row_tiles * col_tiles);
+  int n_split = (int)hs_max<int64_t>(1, hs_min<int64_t>(hs_min<int64_t>(want, max_split), 65535));
+  int64_t cells_per_split = ((N + n_split - 1) / n_split + 255) / 256 * 256;
+  n_split = (int)((N + cells_per_split - 1) / cells_per_split);
+  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_split * n_rows * ldP));
+  dim3 grid(row_tiles, n_split, col_tiles);
+  k_dense_partial<TE, PERM><<<grid, 256, 0, ctx->stream>>>(E, ld, v, perm, index_base, n_rows, N,
+                                                            (const float*)ctx->D32.p, ctx->ldD, G,
+                                                            (int)cells_per_split, ldP, (double*)ctx->part.p);
+  HS_LAUNCH_CHECK(ctx);
+  return launch_rows_epilogue(ctx, (const double*)ctx->part.p, n_split, n_rows, ldP, out);
+}
+
+}  // namespace
+
+int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev, int64_t n_rows,
+               double* out_dev) {
+  return launch_rows_gather<false>(ctx, p_dev, j_dev, x_dev, n_rows, 1, n_rows, 0, out_dev);
+}
+
+int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
+                    const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
+  return launch_rows_gather<true>(ctx, gene_ptr_dev, ind_dev, val_dev, n_sel * (int64_t)n_perm, n_perm, n_sel,
+                                  index_base, out_dev);
+}
+
+int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {
+  return launch_dense<float, false>(ctx, e_dev, ld, nullptr, nullptr, 0, n_genes, out_dev);
+}
+
+int hs_run_dense_f64(hs_ctx* ctx, const double* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {
+  return launch_dense<double, false>(ctx, e_dev, ld, nullptr, nullptr, 0, n_genes, out_dev);
+}
+
+int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm, int index_base,
+                      double* out_dev) {
+  return launch_dense<float, true>(ctx, (const float*)nullptr, 0, v_dev, perm_dev, index_base, n_perm, out_dev);
+}

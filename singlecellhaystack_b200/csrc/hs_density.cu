@@ -1,0 +1,266 @@
+// K1: density stage of haystack_continuous_highD
+//   dist  = get_dist_two_sets(x, grid)            R/haystack_highD.R:17-24, call R/haystack_continuous.R:168
+//   bw    = median(apply(dist, 1, min))           R/haystack_continuous.R:174
+//   D     = exp(-(dist/bw)^2 / 2)                 R/haystack_continuous.R:175-177
+//   Q     = colSums(D [* w]) + 1e-300, / sum      R/haystack_continuous.R:179-186
+// All arithmetic is fp64 (the bandwidth scales every exponent; see DESIGN.md "precision").
+// The density matrix is left resident as fp32, cell-major [N][ldD], for the contraction kernels.
+#include <math.h>
+
+#include "hs_common.cuh"
+
+namespace {
+
+constexpr int kCellsPerBlock = 128;
+constexpr int kJT = 4;  // grid points per register tile in the distance kernel
+
+// ---- squared distances, per-cell minimum and nearest grid point --------------------------------
+// x: [N x d] column-major, grid: [G x d] column-major.  sq: [G][N] (column-major N x G, like R's
+// dist.to.grid) so that both the write here and the read in k_density are coalesced over cells.
+__global__ void __launch_bounds__(kCellsPerBlock)
+k_sqdist(const double* __restrict__ x, int64_t N, int d, const double* __restrict__ grid, int G,
+         int jchunk, double* __restrict__ sq, double* __restrict__ rowmin, int32_t* __restrict__ nearest) {
+  extern __shared__ double gs[];  // [jchunk][d]
+  const int64_t c = (int64_t)blockIdx.x * kCellsPerBlock + threadIdx.x;
+  const bool valid = c < N;
+  const int64_t cc = valid ? c : N - 1;
+  double best = INFINITY;
+  int bestj = 0;
+  for (int j0 = 0; j0 < G; j0 += jchunk) {
+    const int jn = min(jchunk, G - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < jn * d; i += kCellsPerBlock) {
+      const int jj = i / d, k = i - jj * d;
+      gs[i] = grid[(int64_t)(j0 + jj) + (int64_t)k * G];
+    }
+    __syncthreads();
+    for (int jj = 0; jj < jn; jj += kJT) {
+      double s[kJT];
+      const double* g[kJT];
+#pragma unroll
+      for (int t = 0; t < kJT; ++t) {
+        s[t] = 0.0;
+        g[t] = gs + (size_t)min(jj + t, jn - 1) * d;
+      }
+      for (int k = 0; k < d; ++k) {
+        const double xv = x[cc + (int64_t)k * N];
+#pragma unroll
+        for (int t = 0; t < kJT; ++t) {
+          const double diff = xv - g[t][k];
+          s[t] += diff * diff;  // (x-y)^2 summed in order, R/haystack_highD.R:8
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kJT; ++t) {
+        if (jj + t < jn) {
+          const int j = j0 + jj + t;
+          if (valid) sq[(int64_t)j * N + c] = s[t];
+          if (s[t] < best) {  // strict: first minimum wins
+            best = s[t];
+            bestj = j;
+          }
+        }
+      }
+    }
+  }
+  if (valid) {
+    rowmin[c] = sqrt(best);
+    nearest[c] = bestj;
+  }
+}
+
+// ---- exact order statistics of rowmin by MSB-first radix select on the fp64 bit patterns ------
+// (non-negative doubles order like their unsigned bit patterns).  Two ranks are tracked at once:
+// the two middle order statistics R's median() averages for even N.
+struct SelState {
+  unsigned long long prefix[2];
+  long long rank[2];
+  unsigned int hist[2][256];
+};
+
+__global__ void k_sel_init(SelState* st, long long ra, long long rb) {
+  const int t = threadIdx.x;
+  if (t < 2) {
+    st->prefix[t] = 0ull;
+    st->rank[t] = t == 0 ? ra : rb;
+  }
+  for (int i = t; i < 512; i += blockDim.x) (&st->hist[0][0])[i] = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_sel_hist(const unsigned long long* __restrict__ keys, int64_t n, int shift, SelState* st) {
+  __shared__ unsigned int h[2][256];
+  h[0][threadIdx.x] = 0u;
+  h[1][threadIdx.x] = 0u;
+  __syncthreads();
+  const unsigned long long himask = (shift + 8 >= 64) ? 0ull : (~0ull << (shift + 8));
+  const unsigned long long pa = st->prefix[0], pb = st->prefix[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const unsigned long long k = keys[i];
+    const unsigned int dig = (unsigned int)((k >> shift) & 0xFFull);
+    if ((k & himask) == pa) atomicAdd(&h[0][dig], 1u);
+    if ((k & himask) == pb) atomicAdd(&h[1][dig], 1u);
+  }
+  __syncthreads();
+  if (h[0][threadIdx.x]) atomicAdd(&st->hist[0][threadIdx.x], h[0][threadIdx.x]);
+  if (h[1][threadIdx.x]) atomicAdd(&st->hist[1][threadIdx.x], h[1][threadIdx.x]);
+}
+
+__global__ void k_sel_pick(SelState* st, int shift) {
+  const int t = threadIdx.x;
+  if (t < 2) {
+    long long r = st->rank[t];
+    int dig = 255;
+    for (int b = 0; b < 256; ++b) {
+      const long long cnt = st->hist[t][b];
+      if (r < cnt) {
+        dig = b;
+        break;
+      }
+      r -= cnt;
+    }
+    st->rank[t] = r;
+    st->prefix[t] |= ((unsigned long long)dig) << shift;
+    for (int b = 0; b < 256; ++b) st->hist[t][b] = 0u;
+  }
+}
+
+__global__ void k_sel_final(const SelState* st, double* bw) {
+  const double a = __longlong_as_double((long long)st->prefix[0]);
+  const double b = __longlong_as_double((long long)st->prefix[1]);
+  *bw = (st->prefix[0] == st->prefix[1]) ? a : (a + b) / 2.0;  // mean of the two middle values
+}
+
+// ---- density + per-block column sums ------------------------------------------------------------
+__global__ void __launch_bounds__(kCellsPerBlock)
+k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, const double* __restrict__ bw_dev,
+          const double* __restrict__ wq, float* __restrict__ D32, double* __restrict__ dens64,
+          double* __restrict__ qpart) {
+  extern __shared__ unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                               // [128][129]
+  double* qs = reinterpret_cast<double*>(smem_raw + sizeof(float) * 128 * 129 + 8); // [4][128]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t c = (int64_t)blockIdx.x * kCellsPerBlock + tid;
+  const bool valid = c < N;
+  const double bw = *bw_dev;
+  const double w = (valid && wq) ? wq[c] : 1.0;
+  for (int j0 = 0; j0 < ldD; j0 += 128) {
+    const int jn = max(0, min(128, G - j0));        // real columns in this chunk
+    const int jpad = min(128, ldD - j0);            // columns to store (zero padded)
+    for (int jj = 0; jj < jn; ++jj) {
+      double dv = 0.0;
+      if (valid) {
+        const double dist = sqrt(sq[(int64_t)(j0 + jj) * N + c]);
+        const double dn = dist / bw;                // :175
+        dv = exp(-dn * dn / 2);                     // :176-177
+        if (dens64) dens64[(int64_t)(j0 + jj) * N + c] = dv;
+      }
+      tile[tid * 129 + jj] = (float)dv;
+      const double qsum = hs_warp_sum(valid ? dv * w : 0.0);   // :180 / :182
+      if (lane == 0) qs[warp * 128 + jj] = qsum;
+    }
+    for (int jj = jn; jj < jpad; ++jj) tile[tid * 129 + jj] = 0.f;
+    __syncthreads();
+    for (int jj = tid; jj < jn; jj += kCellsPerBlock)
+      qpart[(int64_t)blockIdx.x * G + j0 + jj] = (qs[jj] + qs[128 + jj]) + (qs[256 + jj] + qs[384 + jj]);
+    for (int r = warp; r < kCellsPerBlock; r += 4) {
+      const int64_t cr = (int64_t)blockIdx.x * kCellsPerBlock + r;
+      if (cr < N)
+        for (int jj = lane; jj < jpad; jj += 32) D32[cr * ldD + j0 + jj] = tile[r * 129 + jj];
+    }
+    __syncthreads();
+  }
+}
+
+// Q = (colsum + pseudo) / sum   (R/haystack_continuous.R:184-186); fixed summation order.
+__global__ void __launch_bounds__(256)
+k_q_finalize(const double* __restrict__ qpart, int nblocks, int G, double* __restrict__ Q) {
+  __shared__ double red[256];
+  double local = 0.0;
+  for (int j = threadIdx.x; j < G; j += 256) {
+    double q = 0.0;
+    for (int b = 0; b < nblocks; ++b) q += qpart[(int64_t)b * G + j];
+    q += HS_PSEUDO;
+    Q[j] = q;
+    local += q;
+  }
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  const double total = red[0];
+  for (int j = threadIdx.x; j < G; j += 256) Q[j] = Q[j] / total;
+}
+
+__global__ void k_f64_to_f32(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+}  // namespace
+
+int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n) {
+  if (n <= 0) return HS_OK;
+  const int blocks = (int)hs_min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  k_f64_to_f32<<<blocks, 256, 0, ctx->stream>>>(src, dst, n);
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
+
+int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
+                   const double* wq_dev, bool want_dens64) {
+  const int ldD = (G + 3) & ~3;
+  const int nblocks = (int)((N + kCellsPerBlock - 1) / kCellsPerBlock);
+  HS_TRY(hs_ensure(ctx, ctx->sq, sizeof(double) * (size_t)N * G));
+  HS_TRY(hs_ensure(ctx, ctx->rowmin, sizeof(double) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->nearest, sizeof(int32_t) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->sel, sizeof(SelState) + 64));
+  HS_TRY(hs_ensure(ctx, ctx->qpart, sizeof(double) * (size_t)nblocks * G));
+  HS_TRY(hs_ensure(ctx, ctx->D32, sizeof(float) * (size_t)N * ldD));
+  HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)G + 64));
+  if (want_dens64) HS_TRY(hs_ensure(ctx, ctx->dens64, sizeof(double) * (size_t)N * G));
+  cudaStream_t st = ctx->stream;
+
+  // grid chunk staged in shared memory: <= 64 KB
+  int jchunk = (int)hs_min<int64_t>(G, hs_max<int64_t>(kJT, (64 * 1024) / (sizeof(double) * (size_t)d)));
+  const size_t smem1 = sizeof(double) * (size_t)jchunk * d;
+  if (smem1 > 200 * 1024) return hs_fail(ctx, HS_ERR_INVALID, "n_dims=%d too large for the distance kernel", d);
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_sqdist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  k_sqdist<<<nblocks, kCellsPerBlock, smem1, st>>>(x_dev, N, d, grid_dev, G, jchunk, (double*)ctx->sq.p,
+                                                    (double*)ctx->rowmin.p, (int32_t*)ctx->nearest.p);
+  HS_LAUNCH_CHECK(ctx);
+
+  // exact median of the row minima
+  SelState* sel = (SelState*)ctx->sel.p;
+  double* bw_dev = (double*)((char*)ctx->sel.p + sizeof(SelState));
+  const long long ra = (N - 1) / 2, rb = N / 2;
+  k_sel_init<<<1, 256, 0, st>>>(sel, ra, rb);
+  HS_LAUNCH_CHECK(ctx);
+  const int hblocks = (int)hs_min<int64_t>((N + 255) / 256, (int64_t)ctx->sm_count * 4);
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    k_sel_hist<<<hblocks, 256, 0, st>>>((const unsigned long long*)ctx->rowmin.p, N, shift, sel);
+    HS_LAUNCH_CHECK(ctx);
+    k_sel_pick<<<1, 32, 0, st>>>(sel, shift);
+    HS_LAUNCH_CHECK(ctx);
+  }
+  k_sel_final<<<1, 1, 0, st>>>(sel, bw_dev);
+  HS_LAUNCH_CHECK(ctx);
+
+  const size_t smem2 = sizeof(float) * 128 * 129 + 8 + sizeof(double) * 4 * 128;
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  k_density<<<nblocks, kCellsPerBlock, smem2, st>>>((const double*)ctx->sq.p, N, G, ldD, bw_dev, wq_dev,
+                                                     (float*)ctx->D32.p,
+                                                     want_dens64 ? (double*)ctx->dens64.p : nullptr,
+                                                     (double*)ctx->qpart.p);
+  HS_LAUNCH_CHECK(ctx);
+  k_q_finalize<<<1, 256, 0, st>>>((const double*)ctx->qpart.p, nblocks, G, (double*)ctx->Q.p);
+  HS_LAUNCH_CHECK(ctx);
+
+  HS_CUDA(ctx, cudaMemcpyAsync(&ctx->bw, bw_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+  ctx->N = N;
+  ctx->G = G;
+  ctx->ldD = ldD;
+  return HS_OK;
+}

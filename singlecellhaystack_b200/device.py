@@ -1,0 +1,237 @@
+"""Thin object wrapper over the C ABI: one `DeviceContext` per process and GPU.
+
+Host arrays go in as numpy (R layout: column-major double); the `*_dev` methods take torch CUDA
+tensors and pass their device pointers straight through (torch is plumbing for device memory and
+streams only -- every kernel is in libhaystack_b200.so).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import HaystackLibraryError
+
+__all__ = ["DeviceContext", "HaystackLibraryError"]
+
+
+def _f64_colmajor(a, name):
+    a = np.asarray(a)
+    if a.dtype != np.float64 or not a.flags.f_contiguous:
+        a = np.asfortranarray(a, dtype=np.float64)
+    if a.ndim not in (1, 2):
+        raise ValueError(f"{name} must be 1-D or 2-D")
+    return a
+
+
+def _ptr(a) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(None)
+
+
+def _dptr(t) -> C.c_void_p:
+    """Device pointer of a torch CUDA tensor (or None)."""
+    if t is None:
+        return C.c_void_p(None)
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class DeviceContext:
+    """Owns an `hs_ctx*`.  Not thread-safe (neither is R, the intended caller)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        h = C.c_void_p(None)
+        rc = self._lib.hs_create(int(device), C.byref(h))
+        if rc != _lib.HS_OK:
+            raise HaystackLibraryError(f"hs_create failed ({rc}): {_lib.last_error(None)}")
+        self._h = h
+        self.device = int(device)
+
+    # -- plumbing -----------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.hs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc: int, what: str):
+        if rc != _lib.HS_OK:
+            raise HaystackLibraryError(f"{what} failed ({rc}): {_lib.last_error(self._h)}")
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        self._check(self._lib.hs_set_stream(self._h, C.c_void_p(cuda_stream_ptr or None)), "hs_set_stream")
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self._check(self._lib.hs_synchronize(self._h), "hs_synchronize")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.hs_launch_count(self._h))
+
+    def enable_timers(self, on: bool = True):
+        self._check(self._lib.hs_enable_timers(self._h, int(bool(on))), "hs_enable_timers")
+
+    def last_timers(self) -> dict:
+        buf = (C.c_float * 5)()
+        n = self._lib.hs_last_timers(self._h, buf, 5)
+        names = ["density", "csr", "dense", "perm", "copy"]
+        return {names[i]: float(buf[i]) for i in range(n)}
+
+    @property
+    def shape(self):
+        n, g = C.c_int64(0), C.c_int(0)
+        self._check(self._lib.hs_density_shape(self._h, C.byref(n), C.byref(g)), "hs_density_shape")
+        return int(n.value), int(g.value)
+
+    # -- K1 -----------------------------------------------------------------------------------
+    def density(self, x, grid, w_q=None, want_densities=False, want_nearest=False):
+        """hs_density: x (N,d), grid (G,d) in the same (scaled) space.  Returns dict with
+        bandwidth, Q and optionally densities (N,G) fp64 and nearest (N,) int32 0-based."""
+        x = _f64_colmajor(x, "x")
+        grid = _f64_colmajor(grid, "grid")
+        if x.ndim == 1:
+            x = x.reshape(-1, 1, order="F")
+        if grid.ndim == 1:
+            grid = grid.reshape(-1, 1, order="F")
+        if x.shape[1] != grid.shape[1]:
+            raise ValueError("Coordinates and grid points have different number of columns.")
+        n, d = x.shape
+        g = grid.shape[0]
+        w = None
+        if w_q is not None:
+            w = np.ascontiguousarray(w_q, dtype=np.float64)
+            if w.shape != (n,):
+                raise ValueError("The length of 'weights.advanced.Q' must be the same as the number of rows in 'x'")
+        bw = C.c_double(0.0)
+        q = np.empty(g, dtype=np.float64)
+        dens = np.empty((n, g), dtype=np.float64, order="F") if want_densities else None
+        near = np.empty(n, dtype=np.int32) if want_nearest else None
+        rc = self._lib.hs_density(self._h, _ptr(x), n, d, _ptr(grid), g, _ptr(w), C.byref(bw), _ptr(q),
+                                  _ptr(dens), _ptr(near))
+        self._check(rc, "hs_density")
+        return dict(bandwidth=float(bw.value), Q=q, densities=dens, nearest=near)
+
+    def density_dev(self, x_dev, grid_dev, w_q_dev=None):
+        """x_dev (d,N)-contiguous torch fp64 tensor == column-major N x d; grid_dev likewise (d,G)."""
+        d, n = x_dev.shape
+        d2, g = grid_dev.shape
+        if d != d2:
+            raise ValueError("Coordinates and grid points have different number of columns.")
+        bw = C.c_double(0.0)
+        q = np.empty(g, dtype=np.float64)
+        rc = self._lib.hs_density_dev(self._h, _dptr(x_dev), n, d, _dptr(grid_dev), g, _dptr(w_q_dev),
+                                      C.byref(bw), _ptr(q))
+        self._check(rc, "hs_density_dev")
+        return dict(bandwidth=float(bw.value), Q=q)
+
+    def density_blob_bytes(self) -> int:
+        b = C.c_int64(0)
+        self._check(self._lib.hs_density_blob_bytes(self._h, C.byref(b)), "hs_density_blob_bytes")
+        return int(b.value)
+
+    def density_export_dev(self, blob):
+        self._check(self._lib.hs_density_export_dev(self._h, _dptr(blob), blob.numel() * blob.element_size()),
+                    "hs_density_export_dev")
+
+    def density_import_dev(self, blob):
+        self._check(self._lib.hs_density_import_dev(self._h, _dptr(blob), blob.numel() * blob.element_size()),
+                    "hs_density_import_dev")
+
+    # -- K2/K3 --------------------------------------------------------------------------------
+    def dkl_dense(self, expression) -> np.ndarray:
+        """expression: (M, N) genes x cells; any layout, passed as an R matrix (column-major fp64)."""
+        e = _f64_colmajor(expression, "expression")
+        if e.ndim != 2:
+            raise ValueError("'expression' must be a matrix")
+        m, n = e.shape
+        if n != self.shape[0]:
+            raise ValueError("The number of columns in 'expression' must be the same as the rows in 'x'")
+        out = np.empty(m, dtype=np.float64)
+        self._check(self._lib.hs_dkl_dense(self._h, _ptr(e), m, m, _ptr(out)), "hs_dkl_dense")
+        return out
+
+    def dkl_csr(self, p, j, x) -> np.ndarray:
+        """dgRMatrix slots: p (M+1, int32/int64), j (int32, 0-based), x (float64)."""
+        p = np.ascontiguousarray(p)
+        if p.dtype == np.int64:
+            is64 = 1
+        else:
+            p = np.ascontiguousarray(p, dtype=np.int32)
+            is64 = 0
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        m = p.size - 1
+        out = np.empty(max(m, 0), dtype=np.float64)
+        self._check(self._lib.hs_dkl_csr(self._h, _ptr(p), is64, _ptr(j), _ptr(x), m, _ptr(out)), "hs_dkl_csr")
+        return out
+
+    # -- K4 -----------------------------------------------------------------------------------
+    def dkl_perm_dense(self, v, perm, index_base=1) -> np.ndarray:
+        """v (N,), perm (N, R) column r = sample.int(N).  Returns (R,)."""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        perm = np.asfortranarray(perm, dtype=np.int32)
+        n, r = perm.shape
+        if v.shape != (n,) or n != self.shape[0]:
+            raise ValueError("perm must be n_cells x n_perm and v of length n_cells")
+        out = np.empty(r, dtype=np.float64)
+        self._check(self._lib.hs_dkl_perm_dense(self._h, _ptr(v), _ptr(perm), r, int(index_base), _ptr(out)),
+                    "hs_dkl_perm_dense")
+        return out
+
+    def dkl_perm_csr(self, vals: list, inds: list, index_base=1) -> np.ndarray:
+        """vals[s]: (nnz_s,) values of selected gene s; inds[s]: (nnz_s, R) column r =
+        sample(n_cells, nnz_s).  Returns (S, R) (all.D_KL.randomized)."""
+        s_ = len(vals)
+        if s_ == 0:
+            return np.zeros((0, 0))
+        r = inds[0].shape[1]
+        gp = np.zeros(s_ + 1, dtype=np.int64)
+        for i, v in enumerate(vals):
+            if inds[i].shape != (len(v), r):
+                raise ValueError("inds[s] must be nnz_s x n_perm")
+            gp[i + 1] = gp[i] + len(v)
+        val = np.concatenate([np.asarray(v, dtype=np.float64) for v in vals]) if gp[-1] else np.zeros(0)
+        ind = (np.concatenate([np.asfortranarray(a, dtype=np.int32).ravel(order="F") for a in inds])
+               if gp[-1] else np.zeros(0, dtype=np.int32))
+        out = np.empty((s_, r), dtype=np.float64, order="F")
+        self._check(self._lib.hs_dkl_perm_csr(self._h, _ptr(gp), s_, _ptr(val), _ptr(ind), r, int(index_base),
+                                              _ptr(out)), "hs_dkl_perm_csr")
+        return out
+
+    # -- device-resident variants -------------------------------------------------------------
+    def dkl_csr_dev(self, p_dev, j_dev, x_dev, out_dev):
+        m = p_dev.numel() - 1
+        self._check(self._lib.hs_dkl_csr_dev(self._h, _dptr(p_dev), _dptr(j_dev), _dptr(x_dev), m, _dptr(out_dev)),
+                    "hs_dkl_csr_dev")
+
+    def dkl_perm_csr_dev(self, gene_ptr_dev, val_dev, ind_dev, n_perm, out_dev, index_base=0):
+        s_ = gene_ptr_dev.numel() - 1
+        self._check(self._lib.hs_dkl_perm_csr_dev(self._h, _dptr(gene_ptr_dev), s_, _dptr(val_dev), _dptr(ind_dev),
+                                                  int(n_perm), int(index_base), _dptr(out_dev)),
+                    "hs_dkl_perm_csr_dev")
+
+    def dkl_dense_dev(self, expr_dev, n_genes, ld, out_dev):
+        self._check(self._lib.hs_dkl_dense_dev(self._h, _dptr(expr_dev), int(n_genes), int(ld), _dptr(out_dev)),
+                    "hs_dkl_dense_dev")
+
+    def dkl_perm_dense_dev(self, v_dev, perm_dev, n_perm, out_dev, index_base=0):
+        self._check(self._lib.hs_dkl_perm_dense_dev(self._h, _dptr(v_dev), _dptr(perm_dev), int(n_perm),
+                                                    int(index_base), _dptr(out_dev)), "hs_dkl_perm_dense_dev")
