@@ -75,12 +75,16 @@ int hs_density(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims, const 
                int n_grid, const double* w_q, double* bandwidth_out, double* q_out,
                double* density_out, int32_t* nearest_out);
 
-/* Resident density state, for multi-GPU broadcast by the host layer.  The blob is opaque,
- * device-resident and position independent: export on the rank that ran hs_density, move it
- * with any collective, import on the others. */
-int hs_density_blob_bytes(const hs_ctx* ctx, int64_t* bytes_out);
-int hs_density_export_dev(hs_ctx* ctx, void* dev_dst, int64_t bytes);
-int hs_density_import_dev(hs_ctx* ctx, const void* dev_src, int64_t bytes);
+/* Multi-GPU (one process per GPU): the rank that ran hs_density exposes its resident state, the
+ * other ranks reserve buffers of the same shape, receive into them with any collective (NCCL
+ * broadcast over NVLink in the host layer) and commit.  d_dev: fp32 density matrix, d_bytes long;
+ * q_dev: n_grid doubles of Q followed by one double holding the bandwidth, q_bytes long.
+ * On a context with a resident state of exactly this shape the call only reports the pointers;
+ * otherwise it (re)allocates and marks the state invalid until hs_density_commit. */
+int hs_density_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, void** d_dev, int64_t* d_bytes,
+                       void** q_dev, int64_t* q_bytes);
+/* Declare the buffers filled: reads the bandwidth back from q_dev[n_grid] and validates it. */
+int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid);
 /* Shape of the resident state (0,0 when none). */
 int hs_density_shape(const hs_ctx* ctx, int64_t* n_cells_out, int* n_grid_out);
 

@@ -28,9 +28,8 @@ SIGNATURES = {
     "hs_set_stream": (_int, [_vp, _vp]),
     "hs_synchronize": (_int, [_vp]),
     "hs_density": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
-    "hs_density_blob_bytes": (_int, [_vp, C.POINTER(_i64)]),
-    "hs_density_export_dev": (_int, [_vp, _vp, _i64]),
-    "hs_density_import_dev": (_int, [_vp, _vp, _i64]),
+    "hs_density_buffers": (_int, [_vp, _i64, _int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]),
+    "hs_density_commit": (_int, [_vp, _i64, _int]),
     "hs_density_shape": (_int, [_vp, C.POINTER(_i64), C.POINTER(_int)]),
     "hs_dkl_dense": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_dkl_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp]),

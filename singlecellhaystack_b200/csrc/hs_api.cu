@@ -100,17 +100,6 @@ size_t env_size(const char* name, size_t dflt) {
   return v > 0 ? (size_t)v : dflt;
 }
 
-constexpr int64_t kBlobHeader = 256;
-
-struct BlobHeader {
-  uint64_t magic;
-  int64_t N;
-  int32_t G;
-  int32_t ldD;
-  double bw;
-};
-constexpr uint64_t kBlobMagic = 0x48535442323030ull;  // "HSTB200"
-
 }  // namespace
 
 #pragma GCC visibility push(default)
@@ -284,76 +273,45 @@ int hs_density_shape(const hs_ctx* ctx, int64_t* n_cells_out, int* n_grid_out) {
   return HS_OK;
 }
 
-int hs_density_blob_bytes(const hs_ctx* ctx, int64_t* bytes_out) {
-  if (!ctx || !bytes_out) return hs_fail(nullptr, HS_ERR_INVALID, "null argument");
-  if (ctx->N <= 0) {
-    *bytes_out = 0;
-    return HS_OK;
-  }
-  const int64_t qbytes = ((int64_t)sizeof(double) * ctx->G + 255) / 256 * 256;
-  *bytes_out = kBlobHeader + qbytes + (int64_t)sizeof(float) * ctx->N * ctx->ldD;
-  return HS_OK;
-}
-
-int hs_density_export_dev(hs_ctx* ctx, void* dev_dst, int64_t bytes) {
-  HS_TRY(need_density(ctx));
+int hs_density_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, void** d_dev, int64_t* d_bytes, void** q_dev,
+                       int64_t* q_bytes) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  if (n_cells <= 0 || n_grid <= 0 || n_grid > 1024 || n_cells > 2147483647LL || !d_dev || !q_dev)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_buffers: bad arguments");
   HS_TRY(set_device(ctx));
-  int64_t need = 0;
-  hs_density_blob_bytes(ctx, &need);
-  if (!dev_dst || bytes < need)
-    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_export_dev: need %lld bytes, got %lld", (long long)need,
-                   (long long)bytes);
-  BlobHeader h;
-  memset(&h, 0, sizeof(h));
-  h.magic = kBlobMagic;
-  h.N = ctx->N;
-  h.G = ctx->G;
-  h.ldD = ctx->ldD;
-  h.bw = ctx->bw;
-  char hdr[kBlobHeader];
-  memset(hdr, 0, sizeof(hdr));
-  memcpy(hdr, &h, sizeof(h));
-  cudaStream_t st = ctx->stream;
-  const int64_t qbytes = ((int64_t)sizeof(double) * ctx->G + 255) / 256 * 256;
-  HS_CUDA(ctx, cudaMemcpyAsync(dev_dst, hdr, kBlobHeader, cudaMemcpyHostToDevice, st));
-  HS_CUDA(ctx, cudaStreamSynchronize(st));  // hdr is a stack buffer
-  HS_CUDA(ctx, cudaMemcpyAsync((char*)dev_dst + kBlobHeader, ctx->Q.p, sizeof(double) * ctx->G,
-                               cudaMemcpyDeviceToDevice, st));
-  HS_CUDA(ctx, cudaMemcpyAsync((char*)dev_dst + kBlobHeader + qbytes, ctx->D32.p,
-                               sizeof(float) * (size_t)ctx->N * ctx->ldD, cudaMemcpyDeviceToDevice, st));
-  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  const int ldD = (n_grid + 3) & ~3;
+  if (!(ctx->N == n_cells && ctx->G == n_grid && ctx->ldD == ldD && ctx->D32.p && ctx->Q.p)) {
+    ctx->N = 0;
+    HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)n_grid + 64));
+    HS_TRY(hs_ensure(ctx, ctx->D32, sizeof(float) * (size_t)n_cells * ldD));
+  }
+  *d_dev = ctx->D32.p;
+  *q_dev = ctx->Q.p;
+  if (d_bytes) *d_bytes = (int64_t)sizeof(float) * n_cells * ldD;
+  if (q_bytes) *q_bytes = (int64_t)sizeof(double) * (n_grid + 1);
   return HS_OK;
 }
 
-int hs_density_import_dev(hs_ctx* ctx, const void* dev_src, int64_t bytes) {
+int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   HS_TRY(set_device(ctx));
-  if (!dev_src || bytes < kBlobHeader) return hs_fail(ctx, HS_ERR_INVALID, "hs_density_import_dev: blob too small");
-  cudaStream_t st = ctx->stream;
-  char hdr[kBlobHeader];
-  HS_CUDA(ctx, cudaMemcpyAsync(hdr, dev_src, kBlobHeader, cudaMemcpyDeviceToHost, st));
-  HS_CUDA(ctx, cudaStreamSynchronize(st));
-  BlobHeader h;
-  memcpy(&h, hdr, sizeof(h));
-  if (h.magic != kBlobMagic || h.N <= 0 || h.G <= 0 || h.ldD < h.G)
-    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_import_dev: not a density blob");
-  const int64_t qbytes = ((int64_t)sizeof(double) * h.G + 255) / 256 * 256;
-  const int64_t need = kBlobHeader + qbytes + (int64_t)sizeof(float) * h.N * h.ldD;
-  if (bytes < need)
-    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_import_dev: need %lld bytes, got %lld", (long long)need,
-                   (long long)bytes);
-  ctx->N = 0;
-  HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)h.G + 64));
-  HS_TRY(hs_ensure(ctx, ctx->D32, sizeof(float) * (size_t)h.N * h.ldD));
-  HS_CUDA(ctx, cudaMemcpyAsync(ctx->Q.p, (const char*)dev_src + kBlobHeader, sizeof(double) * h.G,
-                               cudaMemcpyDeviceToDevice, st));
-  HS_CUDA(ctx, cudaMemcpyAsync(ctx->D32.p, (const char*)dev_src + kBlobHeader + qbytes,
-                               sizeof(float) * (size_t)h.N * h.ldD, cudaMemcpyDeviceToDevice, st));
-  HS_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->N = h.N;
-  ctx->G = h.G;
-  ctx->ldD = h.ldD;
-  ctx->bw = h.bw;
+  if (n_cells <= 0 || n_grid <= 0 || !ctx->D32.p || !ctx->Q.p)
+    return hs_fail(ctx, HS_ERR_STATE, "hs_density_commit: call hs_density_buffers first");
+  const int ldD = (n_grid + 3) & ~3;
+  if (ctx->D32.cap < sizeof(float) * (size_t)n_cells * ldD || ctx->Q.cap < sizeof(double) * (size_t)(n_grid + 1))
+    return hs_fail(ctx, HS_ERR_STATE, "hs_density_commit: buffers were reserved for a smaller shape");
+  double bw = 0.0;
+  HS_CUDA(ctx, cudaMemcpyAsync(&bw, (const double*)ctx->Q.p + n_grid, sizeof(double), cudaMemcpyDeviceToHost,
+                               ctx->stream));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (!(bw > 0.0)) {
+    ctx->N = 0;
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_commit: bandwidth %g in the received state is not positive", bw);
+  }
+  ctx->N = n_cells;
+  ctx->G = n_grid;
+  ctx->ldD = ldD;
+  ctx->bw = bw;
   return HS_OK;
 }
 

@@ -258,6 +258,8 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
   k_q_finalize<<<1, 256, 0, st>>>((const double*)ctx->qpart.p, nblocks, G, (double*)ctx->Q.p);
   HS_LAUNCH_CHECK(ctx);
 
+  // the bandwidth rides behind Q so that one collective moves both (hs_density_buffers)
+  HS_CUDA(ctx, cudaMemcpyAsync((double*)ctx->Q.p + G, bw_dev, sizeof(double), cudaMemcpyDeviceToDevice, st));
   HS_CUDA(ctx, cudaMemcpyAsync(&ctx->bw, bw_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
   ctx->N = N;
   ctx->G = G;

@@ -38,6 +38,16 @@ def _dptr(t) -> C.c_void_p:
     return C.c_void_p(t.data_ptr())
 
 
+def _wrap_device_ptr(ptr: int, nbytes: int, dev):
+    """torch uint8 view of device memory owned by the library (so collectives can address it)."""
+    import torch
+
+    class _Cai:
+        __cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+    return torch.as_tensor(_Cai(), device=dev)
+
+
 class DeviceContext:
     """Owns an `hs_ctx*`.  Not thread-safe (neither is R, the intended caller)."""
 
@@ -142,18 +152,30 @@ class DeviceContext:
         self._check(rc, "hs_density_dev")
         return dict(bandwidth=float(bw.value), Q=q)
 
-    def density_blob_bytes(self) -> int:
-        b = C.c_int64(0)
-        self._check(self._lib.hs_density_blob_bytes(self._h, C.byref(b)), "hs_density_blob_bytes")
-        return int(b.value)
+    def density_buffers(self, n_cells: int, n_grid: int):
+        """hs_density_buffers: (d_ptr, d_bytes, q_ptr, q_bytes) of the resident (or freshly reserved) state."""
+        d, q = C.c_void_p(None), C.c_void_p(None)
+        db, qb = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.hs_density_buffers(self._h, int(n_cells), int(n_grid), C.byref(d), C.byref(db),
+                                                 C.byref(q), C.byref(qb)), "hs_density_buffers")
+        return int(d.value), int(db.value), int(q.value), int(qb.value)
 
-    def density_export_dev(self, blob):
-        self._check(self._lib.hs_density_export_dev(self._h, _dptr(blob), blob.numel() * blob.element_size()),
-                    "hs_density_export_dev")
+    def density_commit(self, n_cells: int, n_grid: int):
+        self._check(self._lib.hs_density_commit(self._h, int(n_cells), int(n_grid)), "hs_density_commit")
 
-    def density_import_dev(self, blob):
-        self._check(self._lib.hs_density_import_dev(self._h, _dptr(blob), blob.numel() * blob.element_size()),
-                    "hs_density_import_dev")
+    def density_broadcast(self, n_cells: int, n_grid: int, src: int = 0, group=None):
+        """Multi-GPU exchange step of the path: the density matrix, Q and the bandwidth produced by
+        hs_density on rank `src` are broadcast (torch.distributed: NCCL over NVLink on GPUs) straight
+        between the contexts' own device buffers -- no staging copy."""
+        import torch
+        import torch.distributed as dist
+        d_ptr, d_bytes, q_ptr, q_bytes = self.density_buffers(n_cells, n_grid)
+        dev = torch.device("cuda", self.device)
+        for ptr, nbytes in ((d_ptr, d_bytes), (q_ptr, q_bytes)):
+            t = _wrap_device_ptr(ptr, nbytes, dev)
+            dist.broadcast(t, src=src, group=group)
+        if dist.get_rank(group) != src:
+            self.density_commit(n_cells, n_grid)
 
     # -- K2/K3 --------------------------------------------------------------------------------
     def dkl_dense(self, expression) -> np.ndarray:
@@ -214,6 +236,19 @@ class DeviceContext:
         out = np.empty((s_, r), dtype=np.float64, order="F")
         self._check(self._lib.hs_dkl_perm_csr(self._h, _ptr(gp), s_, _ptr(val), _ptr(ind), r, int(index_base),
                                               _ptr(out)), "hs_dkl_perm_csr")
+        return out
+
+    def dkl_perm_csr_flat(self, gene_ptr, val, ind, n_perm, index_base=1, out=None) -> np.ndarray:
+        """hs_dkl_perm_csr on already flattened host arrays (gene_ptr int64 [S+1], val fp64, ind int32
+        laid out gene by gene as nnz_s x n_perm column-major blocks).  No host-side copies."""
+        gene_ptr = np.ascontiguousarray(gene_ptr, dtype=np.int64)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        ind = np.ascontiguousarray(ind, dtype=np.int32)
+        s_ = gene_ptr.size - 1
+        if out is None:
+            out = np.empty((s_, int(n_perm)), dtype=np.float64, order="F")
+        self._check(self._lib.hs_dkl_perm_csr(self._h, _ptr(gene_ptr), s_, _ptr(val), _ptr(ind), int(n_perm),
+                                              int(index_base), _ptr(out)), "hs_dkl_perm_csr")
         return out
 
     # -- device-resident variants -------------------------------------------------------------

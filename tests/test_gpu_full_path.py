@@ -1,0 +1,106 @@
+"""GPU parity of the whole drop-in path (host layer -> C ABI -> CUDA) against the committed goldens and
+the oracle.  Tolerances are north_star's: integer outputs bit-exact, D_KL 1e-5 relative, log10 p 1e-3."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import haystack_oracle as ho
+from singlecellhaystack_b200 import haystack as hh
+from singlecellhaystack_b200 import sparse as sp
+from singlecellhaystack_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_DKL = 1e-5
+ATOL_LOGP = 1e-3
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def _oracle_stats(expr_sparse):
+    return ho.row_mean_sd(expr_sparse)
+
+
+@pytest.mark.parametrize("form", ["sparse", "dense"])
+def test_toy_full_path_matches_golden(ctx, toy, form):
+    seed = int(toy["seed"])
+    coord, expr = toy["coord"], toy["expression"]
+    xs, center, sc = ho.scale_coords(coord)
+    stats = ho.row_mean_sd(ho.RowSparse.from_dense(expr)) if form == "sparse" else ho.row_mean_sd(expr)
+    e = sp.as_CsparseMatrix(expr) if form == "sparse" else expr      # dgCMatrix in, as users hold it
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = hh.haystack(coord, e, grid_coord=toy["grid100"], gene_names=list(toy["gene_names"]),
+                          perm_source=synth.perm_source(seed), row_stats=stats,
+                          cv_folds=(synth.cv_folds(seed, 0, 100), synth.cv_folds(seed, 1, 100)), ctx=ctx,
+                          verbose=False)
+    r = res["results"]
+    assert list(r.columns) == ["D_KL", "log.p.vals", "log.p.adj"] and r.shape == (500, 3)
+    assert _rel(r["D_KL"].values, toy["dkl100"]) < RTOL_DKL
+    info = res["info"]
+    assert info["method"] == "continuous_highD"
+    gold_rand = toy["full_KLD_rand"] if form == "sparse" else toy["fulld_KLD_rand"]
+    gold_logp = toy["full_log_p"] if form == "sparse" else toy["fulld_log_p"]
+    if form == "sparse":
+        np.testing.assert_array_equal(info["randomization"]["genes_to_randomize"], toy["full_genes_to_randomize"] + 1)
+    assert _rel(info["randomization"]["KLD_rand"], gold_rand) < RTOL_DKL
+    assert np.max(np.abs(r["log.p.vals"].values - gold_logp)) < ATOL_LOGP
+    np.testing.assert_allclose(r["log.p.adj"].values, np.minimum(0, r["log.p.vals"].values + np.log10(500)))
+    np.testing.assert_allclose(info["grid_coordinates"], toy["grid100"] * sc + center, rtol=1e-14)
+    np.testing.assert_allclose(info["coord_mean"], center)
+    assert info["densities"].shape == (601, 100)
+    top = hh.show_result_haystack(res, n=10)
+    assert top["log.p.vals"].is_monotonic_increasing and len(top) == 10
+
+
+def test_reference_structural_assertions(ctx, toy):
+    """tests/testthat/test-haystack_continuous.R:6-15 and test-haystack_sparse.R:4-15: grid.points = 60,
+    own grid selection and random draws; only structure is asserted, as in the reference."""
+    for method in ("centroid", "seeding"):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = hh.haystack_continuous_highD(toy["coord"], sp.as_CsparseMatrix(toy["expression"]), grid_points=60,
+                                               grid_method=method, rng=123, ctx=ctx, verbose=False,
+                                               gene_names=list(toy["gene_names"]))
+        assert isinstance(res, dict) and isinstance(res, hh.Haystack)
+        assert list(res.keys()) == ["results", "info"]
+        assert res["results"].shape == (500, 3)
+        assert res["info"]["grid_coordinates"].shape == (60, 2)
+        assert np.isfinite(res["results"]["D_KL"].values).all()
+        # the vignette's strongest genes come out on top with any reasonable grid
+        top = set(hh.show_result_haystack(res, n=50).index)
+        assert len(top & {"gene_79", "gene_497", "gene_242", "gene_275", "gene_62"}) >= 4
+
+
+@pytest.mark.parametrize("n,d,g,m,rho", [(20000, 10, 100, 256, 0.08), (5000, 1, 37, 128, 0.3), (3000, 50, 130, 64, 0.02)])
+def test_synthetic_csr_parity(ctx, n, d, g, m, rho):
+    x, labels = synth.make_embedding(n, d)
+    xs, _, _ = synth.scale_coords(x)
+    grid = synth.make_grid(xs, g)
+    p, j, v = synth.make_csr_numpy(m, n, rho, labels)
+    ref = ho.density_stage(xs, grid)
+    out = ctx.density(xs, grid, want_nearest=True)
+    assert abs(out["bandwidth"] - ref["bandwidth"]) <= 1e-12 * ref["bandwidth"]
+    np.testing.assert_array_equal(out["nearest"], ref["nearest"])
+    np.testing.assert_allclose(out["Q"], ref["Q"], rtol=1e-9)
+    want = ho.dkl_observed(ho.RowSparse(p=p, j=j, x=v, shape=(m, n)), ref["density"], ref["Q"])
+    got = ctx.dkl_csr(p, j, v)
+    assert _rel(got, want) < RTOL_DKL
+    # dense form of the same rows
+    dense = ho.RowSparse(p=p, j=j, x=v, shape=(m, n)).to_dense()
+    got_d = ctx.dkl_dense(dense[:32])
+    assert _rel(got_d, want[:32]) < RTOL_DKL
+    # randomized, a few genes
+    src = synth.perm_source(7)
+    vals, ids_o, ids_d = [], [], []
+    for gi in range(4):
+        val = v[p[gi]:p[gi + 1]]
+        ids = src("sparse", gi, n, val.size, 10)
+        vals.append(val)
+        ids_o.append(ids)
+        ids_d.append(np.asfortranarray(ids.T))
+    want_r = ho.dkl_randomized_sparse(vals, ids_o, ref["density"], ref["Q"])
+    assert _rel(ctx.dkl_perm_csr(vals, ids_d, index_base=1), want_r) < RTOL_DKL
