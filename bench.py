@@ -363,7 +363,9 @@ def run_b200(a):
     setup_s = time.perf_counter() - t_setup
 
     ctx = DeviceContext(local)
-    ctx.use_torch_stream()
+    work_stream = torch.cuda.Stream(device=dev)          # the library and the timing events share it
+    torch.cuda.set_stream(work_stream)
+    ctx.use_torch_stream(work_stream)
     dkl = torch.empty(m_local, dtype=torch.float64, device=dev)
     dkl_rand = torch.empty(max(n_sel_local * r_loc, 1), dtype=torch.float64, device=dev)
     dkl_all = torch.empty(m_total, dtype=torch.float64, device=dev) if world > 1 else dkl

@@ -158,7 +158,7 @@ void hs_destroy(hs_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->D32, &ctx->Q, &ctx->sq, &ctx->rowmin, &ctx->nearest, &ctx->sel, &ctx->qpart,
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
-                    &ctx->ptrs, &ctx->dense_in};
+                    &ctx->ptrs, &ctx->dense_in, &ctx->spmm_ws, &ctx->cols32};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -318,81 +318,102 @@ int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
 // ------------------------------------------------------------------------------------------------
 // observed D_KL, host pointers
 // ------------------------------------------------------------------------------------------------
-// Generic double-buffered staging loop shared by hs_dkl_csr and hs_dkl_perm_csr.
-//   units        : rows (CSR) or selected genes (perm)
-//   hp[u]        : prefix offsets (values per unit); ids per unit = values * ids_per_value
-struct ChunkPlan {
-  std::vector<int64_t> begin;  // unit index where each chunk starts; last entry = n_units
-};
-
-static ChunkPlan plan_chunks(const std::vector<int64_t>& hp, int64_t ids_per_value, size_t target_ids) {
-  ChunkPlan pl;
-  const int64_t n = (int64_t)hp.size() - 1;
-  int64_t u = 0;
-  pl.begin.push_back(0);
-  while (u < n) {
-    int64_t e = u + 1;
-    while (e < n && (size_t)((hp[e + 1] - hp[u]) * ids_per_value) <= target_ids) ++e;
-    pl.begin.push_back(e);
-    u = e;
-  }
-  return pl;
-}
-
-static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_t* ids, const double* vals,
-                       int64_t ids_per_value, bool perm, int n_perm, int index_base, double* host_out,
-                       int timer_slot) {
-  const int64_t n_units = (int64_t)hp.size() - 1;
-  const int64_t n_out = perm ? n_units * n_perm : n_units;
-  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)std::max<int64_t>(n_out, 1)));
+// Host-pointer sparse entry points: upload the whole batch (ids as they are, values converted
+// fp64 -> fp32 on the device through a double-buffered staging area fed by a second stream), then ONE
+// launch over all rows -- the contraction kernels need many rows per launch to fill the machine.
+// If the batch does not fit into free device memory the units are processed in several batches.
+//   hp[u]  : prefix offsets in values per unit (row or selected gene); ids per unit = values * ipv
+static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const int32_t* ids, const double* vals,
+                          int64_t ipv, bool perm, int n_perm, int index_base, double* dev_out, int timer_slot) {
+  const int64_t v0 = hp[0], n_vals = hp[n_units] - v0, n_ids = n_vals * ipv;
+  const size_t chunk = env_size("HS_STAGE_VALUES", (size_t)16 << 20);   // values per staging buffer
   HS_TRY(hs_ensure(ctx, ctx->ptrs, sizeof(int64_t) * (size_t)(n_units + 1)));
-  const size_t target = env_size("HS_STAGE_IDS", (size_t)32 << 20);
-  ChunkPlan pl = plan_chunks(hp, ids_per_value, target);
-  int64_t max_vals = 0;
-  for (size_t k = 0; k + 1 < pl.begin.size(); ++k)
-    max_vals = std::max(max_vals, hp[pl.begin[k + 1]] - hp[pl.begin[k]]);
-  for (int b = 0; b < 2; ++b) {
-    HS_TRY(hs_ensure(ctx, ctx->stage_j[b], sizeof(int32_t) * (size_t)(max_vals * ids_per_value)));
-    HS_TRY(hs_ensure(ctx, ctx->stage_x[b], sizeof(double) * (size_t)max_vals));
-  }
-  HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)max_vals * 2 + 64));
-  float* v32[2] = {(float*)ctx->vals32.p, (float*)ctx->vals32.p + max_vals};
-
+  HS_TRY(hs_ensure(ctx, ctx->cols32, sizeof(int32_t) * (size_t)hs_max<int64_t>(n_ids, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)hs_max<int64_t>(n_vals, 1)));
+  const size_t stage_vals = (size_t)hs_min<int64_t>((int64_t)chunk, hs_max<int64_t>(n_vals, 1));
+  for (int b = 0; b < 2; ++b) HS_TRY(hs_ensure(ctx, ctx->stage_x[b], sizeof(double) * stage_vals));
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
-  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, hp.data(), sizeof(int64_t) * (size_t)(n_units + 1),
-                               cudaMemcpyHostToDevice, st));
-  ScopedTimer tm(ctx, timer_slot);
-  const int64_t base0 = hp[0];
-  for (size_t k = 0; k + 1 < pl.begin.size(); ++k) {
-    const int b = (int)(k & 1);
-    const int64_t u0 = pl.begin[k], u1 = pl.begin[k + 1];
-    const int64_t v0 = hp[u0], nv = hp[u1] - hp[u0];
+
+  // row pointers rebased to the uploaded arrays
+  std::vector<int64_t> rel((size_t)n_units + 1);
+  for (int64_t u = 0; u <= n_units; ++u) rel[u] = hp[u] - v0;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, rel.data(), sizeof(int64_t) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
+  // the copy stream must not overtake work of earlier calls that still reads the buffers
+  HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
+  HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));
+
+  ScopedTimer tcopy(ctx, HS_T_COPY);
+  // values: staged fp64 -> fp32
+  int k = 0;
+  for (int64_t off = 0; off < n_vals; off += (int64_t)stage_vals, ++k) {
+    const int b = k & 1;
+    const int64_t n = hs_min<int64_t>((int64_t)stage_vals, n_vals - off);
     if (k >= 2) HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[b], 0));
-    if (nv > 0) {
-      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_j[b].p, ids + (v0 - base0) * ids_per_value,
-                                   sizeof(int32_t) * (size_t)(nv * ids_per_value), cudaMemcpyHostToDevice, cs));
-      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[b].p, vals + (v0 - base0), sizeof(double) * (size_t)nv,
-                                   cudaMemcpyHostToDevice, cs));
-    }
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[b].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
     HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], cs));
     HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[b], 0));
-    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, v32[b], nv));
-    // kernels index with the absolute offsets in ptrs[]: shift the chunk bases accordingly
-    const int32_t* ids_dev = (const int32_t*)ctx->stage_j[b].p - v0 * ids_per_value;
-    const float* val_dev = v32[b] - v0;
-    const int64_t* ptr_dev = (const int64_t*)ctx->ptrs.p + u0;
-    if (perm) {
-      HS_TRY(hs_run_perm_csr(ctx, ptr_dev, u1 - u0, val_dev, ids_dev, n_perm, index_base,
-                             (double*)ctx->out.p + u0));
-    } else {
-      HS_TRY(hs_run_csr(ctx, ptr_dev, ids_dev, val_dev, u1 - u0, (double*)ctx->out.p + u0));
-    }
+    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, (float*)ctx->vals32.p + off, n));
     HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
   }
+  // ids: straight into place, in pieces so that pageable sources do not serialise one huge copy
+  const int64_t piece = (int64_t)64 << 20;
+  for (int64_t off = 0; off < n_ids; off += piece) {
+    const int64_t n = hs_min<int64_t>(piece, n_ids - off);
+    HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 * ipv + off, sizeof(int32_t) * (size_t)n,
+                                 cudaMemcpyHostToDevice, cs));
+  }
+  HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[0], cs));
+  HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[0], 0));
+  tcopy.stop();
+
+  ScopedTimer tm(ctx, timer_slot);
+  if (perm)
+    HS_TRY(hs_run_perm_csr(ctx, (const int64_t*)ctx->ptrs.p, n_units, (const float*)ctx->vals32.p,
+                           (const int32_t*)ctx->cols32.p, n_perm, index_base, dev_out));
+  else
+    HS_TRY(hs_run_csr(ctx, (const int64_t*)ctx->ptrs.p, (const int32_t*)ctx->cols32.p, (const float*)ctx->vals32.p,
+                      n_units, dev_out));
   tm.stop();
-  if (n_out > 0)
-    HS_CUDA(ctx, cudaMemcpyAsync(host_out, ctx->out.p, sizeof(double) * (size_t)n_out, cudaMemcpyDeviceToHost, st));
-  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
+// Split the units into batches that fit into device memory and run them one after the other.
+// Each batch b covers units [ub, ue) and writes `out_per_unit` doubles per unit: contiguous for CSR rows;
+// for the permutation form a batch-local (ue-ub) x n_perm column-major block that is re-laid out on the host.
+static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_t* ids, const double* vals,
+                       int64_t ipv, bool perm, int n_perm, int index_base, double* host_out, int timer_slot) {
+  const int64_t n_units = (int64_t)hp.size() - 1;
+  const int64_t per_unit = perm ? n_perm : 1;
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)hs_max<int64_t>(n_units * per_unit, 1)));
+  size_t free_b = 0, total_b = 0;
+  HS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  // bytes already held by the grow-only upload buffers count as available
+  free_b += ctx->cols32.cap + ctx->vals32.cap;
+  const double budget = (double)env_size("HS_UPLOAD_BUDGET", (size_t)(0.80 * (double)free_b));
+  const double bytes_per_value = 4.0 * (double)ipv + 4.0;
+  std::vector<double> tmp;
+  cudaStream_t st = ctx->stream;
+  int64_t ub = 0;
+  while (ub < n_units) {
+    int64_t ue = ub + 1;
+    while (ue < n_units && (double)(hp[ue + 1] - hp[ub]) * bytes_per_value <= budget) ++ue;
+    double* dev_out = (double*)ctx->out.p + ub * per_unit;
+    HS_TRY(upload_and_run(ctx, hp.data() + ub, ue - ub, ids, vals, ipv, perm, n_perm, index_base,
+                          dev_out, timer_slot));
+    if (!perm || (ub == 0 && ue == n_units)) {
+      HS_CUDA(ctx, cudaMemcpyAsync(host_out + ub * per_unit, dev_out, sizeof(double) * (size_t)((ue - ub) * per_unit),
+                                   cudaMemcpyDeviceToHost, st));
+      HS_CUDA(ctx, cudaStreamSynchronize(st));
+    } else {
+      tmp.resize((size_t)((ue - ub) * per_unit));
+      HS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), dev_out, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, st));
+      HS_CUDA(ctx, cudaStreamSynchronize(st));
+      for (int r = 0; r < n_perm; ++r)
+        for (int64_t s = 0; s < ue - ub; ++s)
+          host_out[(ub + s) + (int64_t)r * n_units] = tmp[(size_t)s + (size_t)r * (size_t)(ue - ub)];
+    }
+    ub = ue;
+  }
   return HS_OK;
 }
 
@@ -408,8 +429,8 @@ int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const 
   for (int64_t i = 0; i < n_genes; ++i)
     if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: row pointers must be non-decreasing");
   if (hp[n_genes] > hp[0] && (!j || !x)) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: j/x are NULL");
-  // j and x are addressed from element hp[0] of the caller's slots
-  return staged_rows(ctx, hp, j + hp[0], x + hp[0], 1, false, 1, 0, dkl_out, HS_T_CSR);
+  // j and x are the caller's whole slots; rows start at element hp[0]
+  return staged_rows(ctx, hp, j, x, 1, false, 1, 0, dkl_out, HS_T_CSR);
 }
 
 int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, const int32_t* ind,
@@ -424,26 +445,7 @@ int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const d
   for (int64_t i = 0; i < n_sel; ++i)
     if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: gene_ptr must be non-decreasing");
   if (hp[n_sel] > 0 && (!val || !ind)) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: val/ind are NULL");
-  // The kernel writes out[s + r * n_sel_chunk]; run chunk-local column-major blocks into ctx->out and
-  // let staged_rows copy back.  To keep the global layout n_sel x n_perm column-major we need one chunk
-  // or a re-layout; do the re-layout on the host for multi-chunk runs.
-  std::vector<double> tmp;
-  const size_t target = env_size("HS_STAGE_IDS", (size_t)32 << 20);
-  ChunkPlan pl = plan_chunks(hp, n_perm, target);
-  if (pl.begin.size() == 2) return staged_rows(ctx, hp, ind, val, n_perm, true, n_perm, index_base, out, HS_T_PERM);
-  // multi-chunk: run each chunk as its own call (each produces a chunk-local column-major block)
-  for (size_t k = 0; k + 1 < pl.begin.size(); ++k) {
-    const int64_t u0 = pl.begin[k], u1 = pl.begin[k + 1];
-    std::vector<int64_t> sub(hp.begin() + u0, hp.begin() + u1 + 1);
-    const int64_t off = sub[0];
-    for (auto& v : sub) v -= off;
-    tmp.assign((size_t)(u1 - u0) * n_perm, 0.0);
-    HS_TRY(staged_rows(ctx, sub, ind + off * n_perm, val + off, n_perm, true, n_perm, index_base, tmp.data(),
-                       HS_T_PERM));
-    for (int r = 0; r < n_perm; ++r)
-      for (int64_t s = 0; s < u1 - u0; ++s) out[(u0 + s) + (int64_t)r * n_sel] = tmp[(size_t)s + (size_t)r * (u1 - u0)];
-  }
-  return HS_OK;
+  return staged_rows(ctx, hp, ind, val, n_perm, true, n_perm, index_base, out, HS_T_PERM);
 }
 
 int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* dkl_out) {

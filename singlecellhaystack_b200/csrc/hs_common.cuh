@@ -60,6 +60,8 @@ struct hs_ctx {
   DevBuf vals32;    // fp32 values
   DevBuf ptrs;      // int64 row pointers
   DevBuf dense_in;  // uploaded dense expression (fp64 col-major)
+  DevBuf spmm_ws;   // slab kernel: flags, sort keys, slot table, cub workspace
+  DevBuf cols32;    // uploaded column / cell ids (host-pointer entry points)
   void* pinned = nullptr;      // small pinned host bounce buffer
   size_t pinned_cap = 0;
 };
@@ -96,6 +98,10 @@ int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes);
 int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
                    const double* wq_dev, bool want_dens64);
 // contraction kernels (hs_contract.cu)
+// slab-staged sparse contraction (hs_spmm.cu); see there for the arguments
+int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
+                     const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
+                     const int** flag_dev_out);
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,
                int64_t n_rows, double* out_dev);
 int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,

@@ -25,7 +25,9 @@ __global__ void __launch_bounds__(256)
 k_rows_gather_kl(const int64_t* __restrict__ ptr, const int32_t* __restrict__ cols,
                  const float* __restrict__ vals, int64_t n_rows, int n_perm, int64_t n_sel, int col_base,
                  const float* __restrict__ D, int ldD, int G, int64_t n_cells, const double* __restrict__ Q,
-                 double* __restrict__ out) {
+                 const int* __restrict__ run_if_flag, double* __restrict__ out) {
+  // chained behind the slab kernel: only runs when that kernel met rows it cannot handle
+  if (run_if_flag && !(*run_if_flag & 1)) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -219,7 +221,7 @@ k_rows_epilogue(const double* __restrict__ part, int n_split, int64_t n_rows, in
 
 template <bool PERM>
 int launch_rows_gather(hs_ctx* ctx, const int64_t* ptr, const int32_t* cols, const float* vals,
-                       int64_t n_rows, int n_perm, int64_t n_sel, int col_base, double* out) {
+                       int64_t n_rows, int n_perm, int64_t n_sel, int col_base, const int* run_if_flag, double* out) {
   if (n_rows <= 0) return HS_OK;
   const int G = ctx->G;
   const int nacc = (G + 31) / 32;
@@ -230,7 +232,7 @@ int launch_rows_gather(hs_ctx* ctx, const int64_t* ptr, const int32_t* cols, con
 #define HS_GATHER_CASE(NA)                                                                          \
   case NA:                                                                                          \
     k_rows_gather_kl<NA, PERM><<<blocks, 256, 0, ctx->stream>>>(ptr, cols, vals, n_rows, n_perm, n_sel, \
-                                                                col_base, D, ctx->ldD, G, ctx->N, Q, out); \
+                                                                col_base, D, ctx->ldD, G, ctx->N, Q, run_if_flag, out); \
     break;
   switch (nacc) {
     HS_GATHER_CASE(1)
@@ -244,10 +246,10 @@ int launch_rows_gather(hs_ctx* ctx, const int64_t* ptr, const int32_t* cols, con
     default:
       if (nacc <= 16) {
         k_rows_gather_kl<16, PERM><<<blocks, 256, 0, ctx->stream>>>(ptr, cols, vals, n_rows, n_perm, n_sel,
-                                                                    col_base, D, ctx->ldD, G, ctx->N, Q, out);
+                                                                    col_base, D, ctx->ldD, G, ctx->N, Q, run_if_flag, out);
       } else if (nacc <= 32) {
         k_rows_gather_kl<32, PERM><<<blocks, 256, 0, ctx->stream>>>(ptr, cols, vals, n_rows, n_perm, n_sel,
-                                                                    col_base, D, ctx->ldD, G, ctx->N, Q, out);
+                                                                    col_base, D, ctx->ldD, G, ctx->N, Q, run_if_flag, out);
       } else {
         return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d exceeds the supported maximum of 1024", G);
       }
@@ -305,13 +307,18 @@ int launch_dense(hs_ctx* ctx, const TE* E, int64_t ld, const float* v, const int
 
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev, int64_t n_rows,
                double* out_dev) {
-  return launch_rows_gather<false>(ctx, p_dev, j_dev, x_dev, n_rows, 1, n_rows, 0, out_dev);
+  if (n_rows <= 0) return HS_OK;
+  // slab-staged kernel; rows it flags (ids not ascending / negative) are redone by the gather kernel,
+  // chained on the device-side flag so no host round trip is needed
+  const int* flag = nullptr;
+  HS_TRY(hs_run_slab_spmm(ctx, false, p_dev, n_rows, 1, j_dev, x_dev, 0, out_dev, &flag));
+  return launch_rows_gather<false>(ctx, p_dev, j_dev, x_dev, n_rows, 1, n_rows, 0, flag, out_dev);
 }
 
 int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
                     const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
   return launch_rows_gather<true>(ctx, gene_ptr_dev, ind_dev, val_dev, n_sel * (int64_t)n_perm, n_perm, n_sel,
-                                  index_base, out_dev);
+                                  index_base, nullptr, out_dev);
 }
 
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {

@@ -1,0 +1,609 @@
+// K3 / K4-sparse: sparse-row x density-matrix contraction with shared-memory staged density slabs.
+//   P[row, :] = sum_i val[i] * D[col[i], :]        R/haystack_continuous.R:596 (colSums(D[ind,] * val))
+//
+// Design (DESIGN.md "K3"): the density matrix D ([N][ldD] fp32, cell-major) is streamed through shared
+// memory one slab of S cells at a time with cp.async.bulk + mbarriers (two buffers; warp 0 issues the
+// requests between its own rows).
+// Every consumer warp owns K rows for the whole kernel and keeps their fp32 partial column sums in
+// registers (lane l holds columns 4l..4l+3 of each of its K rows).  For each slab a warp visits only
+// those of its rows whose next stored column falls inside the slab, reads the row's (col, val) run in
+// coalesced batches of 32, broadcasts them through a per-warp scratch line and gathers D rows from
+// the slab with one LDS.128 per non-zero.  fp32 partials are flushed into fp64 sums (global, L2
+// resident) every kFlushNnz non-zeros, so the accumulation error stays ~1e-7 relative.
+// Rows are dealt to (CTA, warp) bins in snake order of descending length, so bins carry equal work
+// and all CTAs walk the slabs at the same pace (the slab a CTA needs is then usually still in L2).
+// The fused KL epilogue runs in a second tiny kernel over the fp64 sums (P never leaves L2 as fp32).
+//
+// Requirement: within a row the stored columns must be non-decreasing at slab granularity (Matrix
+// keeps dgRMatrix@j ascending).  Violations and negative ids are detected and flagged; the caller
+// then runs the order-independent gather kernel (hs_contract.cu) instead.
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+
+#include "hs_common.cuh"
+
+namespace {
+
+constexpr int kMaxWarps = 16;                  // warps per CTA: 16 (128 registers per thread) or 12 (168)
+constexpr int kFlushNnz = 512;                 // fp32 -> fp64 flush interval (non-zeros per row)
+constexpr int kMaxSmem = 232448;               // 227 KB opt-in limit per CTA on sm_100
+
+// ---- PTX helpers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (TMA engine, no tensor map)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// shared-space accesses by 32-bit address (keeps the generic->shared conversion out of the hot loop)
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
+// ---- slot table ------------------------------------------------------------------------------------
+// One slot = one row assigned to (tile, warp, k).  Built on the device from the row pointers.
+struct Slots {
+  int64_t* coff;   // offset of the row's first column id in cols[]
+  int64_t* voff;   // offset of the row's first value in vals[]
+  int32_t* len;    // stored entries (0 for an empty slot)
+  int32_t* row;    // row index (-1 for an empty slot)
+};
+
+// PERM == false: CSR row r: cols/vals at ptr[r].  PERM == true: row = s * n_perm + r, gene s owns
+// vals[ptr[s] .. ptr[s+1]) and ids at cols[ptr[s] * n_perm + r * nnz_s ..) (R/haystack_continuous.R:275).
+template <bool PERM>
+__global__ void k_row_len(const int64_t* __restrict__ ptr, int64_t n_rows, int n_perm, uint32_t* __restrict__ keys,
+                          int32_t* __restrict__ rows, int* __restrict__ flags) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int64_t s = PERM ? i / n_perm : i;
+  const int64_t l = ptr[s + 1] - ptr[s];
+  if (l > 0x7fffffffLL || l < 0) atomicOr(flags, 2);
+  keys[i] = (uint32_t)hs_min<int64_t>(hs_max<int64_t>(l, 0), 0x7fffffffLL);
+  rows[i] = (int32_t)i;
+}
+
+template <bool PERM>
+__global__ void k_build_slots(const int64_t* __restrict__ ptr, const int32_t* __restrict__ sorted_rows,
+                              int64_t n_rows, int n_perm, int n_bins, int K, Slots sl) {
+  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= (int64_t)n_bins * K) return;
+  const int bin = (int)(slot / K), k = (int)(slot - (int64_t)bin * K);
+  const int64_t i = (int64_t)k * n_bins + ((k & 1) ? (n_bins - 1 - bin) : bin);   // snake deal
+  int64_t co = 0, vo = 0;
+  int32_t len = 0, row = -1;
+  if (i < n_rows) {
+    row = sorted_rows[i];
+    if (PERM) {
+      const int64_t s = row / n_perm, r = row - s * n_perm;
+      const int64_t g0 = ptr[s], nnz = ptr[s + 1] - g0;
+      co = g0 * n_perm + r * nnz;
+      vo = g0;
+      len = (int32_t)nnz;
+    } else {
+      co = vo = ptr[row];
+      len = (int32_t)(ptr[row + 1] - ptr[row]);
+    }
+  }
+  sl.coff[slot] = co;
+  sl.voff[slot] = vo;
+  sl.len[slot] = len;
+  sl.row[slot] = row;
+}
+
+// ---- main kernel -----------------------------------------------------------------------------------
+struct SpmmParams {
+  Slots sl;
+  const int32_t* cols;
+  const float* vals;
+  int col_base;            // 0 or 1 (R indices)
+  const float* D;          // [N][ldD]
+  int ldD;                 // multiple of 4
+  int64_t N;
+  int slab_cells;          // S
+  int64_t seg_cells;       // cells per grid.y segment (multiple of S)
+  int n_seg;
+  double* P64;             // [n_rows][ldP] fp64 column sums (zeroed by the caller)
+  int ldP;
+  int* flags;              // bit 0: order violation / negative id -> caller falls back
+};
+
+template <int NV, int K>
+__device__ __forceinline__ void flush_row(float (&acc)[4 * NV], double* __restrict__ prow, int lane, int ldD,
+                                          bool atomic) {
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c0 = 4 * (lane + 32 * v);
+    if (c0 < ldD) {
+      if (atomic) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(prow + c0 + e, (double)acc[4 * v + e]);
+      } else {
+        double2 a = *reinterpret_cast<double2*>(prow + c0);
+        double2 b = *reinterpret_cast<double2*>(prow + c0 + 2);
+        a.x += (double)acc[4 * v + 0];
+        a.y += (double)acc[4 * v + 1];
+        b.x += (double)acc[4 * v + 2];
+        b.y += (double)acc[4 * v + 3];
+        *reinterpret_cast<double2*>(prow + c0) = a;
+        *reinterpret_cast<double2*>(prow + c0 + 2) = b;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[4 * v + e] = 0.f;
+  }
+}
+
+template <int NV, int K, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = p.slab_cells, ldD = p.ldD;
+  const size_t slab_bytes = (size_t)S * ldD * sizeof(float);
+  unsigned char* slab0 = smem;
+  uint2* scratch = reinterpret_cast<uint2*>(smem + 2 * slab_bytes);                    // [kMaxWarps][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * slab_bytes + kMaxWarps * 32 * sizeof(uint2));
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[2]);
+
+  const int64_t c_begin = (int64_t)blockIdx.y * p.seg_cells;
+  const int64_t c_end = hs_min<int64_t>(p.N, c_begin + p.seg_cells);
+  const int n_slabs = (int)((c_end - c_begin + S - 1) / S);
+
+  if (threadIdx.x == 0) {
+    mbar_init(full0, 1);
+    mbar_init(full0 + 8, 1);
+    mbar_init(empty0, kWarps);
+    mbar_init(empty0 + 8, kWarps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---------------- producer duty (warp 0, between its own rows) ----------------
+  // Slab s goes into buffer s & 1 once every warp has released slab s - 2 and that fill has landed
+  // (a warp that skipped a slab releases it without ever waiting for the data).
+  int load_s = 0;   // next slab to request; only meaningful in warp 0
+  auto issue = [&](int s) {
+    if (lane == 0) {
+      const int b = s & 1;
+      const int64_t c0 = c_begin + (int64_t)s * S;
+      const uint32_t bytes = (uint32_t)(hs_min<int64_t>(S, c_end - c0) * ldD * sizeof(float));
+      mbar_arrive_expect_tx(full0 + 8 * b, bytes);
+      bulk_g2s(smem_u32(slab0 + b * slab_bytes), p.D + c0 * ldD, bytes, full0 + 8 * b);
+    }
+  };
+  auto produce = [&](int upto, bool block) {   // request slabs < upto; warp-uniform control flow
+    while (load_s < upto && load_s < n_slabs) {
+      if (load_s >= 2) {
+        const int b = load_s & 1;
+        const uint32_t par = ((load_s >> 1) - 1) & 1;
+        if (block) {
+          mbar_wait(empty0 + 8 * b, par);
+          mbar_wait(full0 + 8 * b, par);
+        } else {
+          const bool ready = mbar_test(empty0 + 8 * b, par) && mbar_test(full0 + 8 * b, par);
+          if (!__shfl_sync(0xffffffffu, (int)ready, 0)) break;
+        }
+      }
+      issue(load_s);
+      ++load_s;
+    }
+  };
+  if (warp == 0) produce(2, true);
+
+  // ---------------- consumers ----------------
+  // lane k (< K) carries the cursor of this warp's k-th row
+  const int64_t bin = (int64_t)blockIdx.x * kWarps + warp;
+  int64_t coff = 0, voff = 0;
+  int len = 0, row = -1, pos = 0, next_col = 0x7fffffff, cnt = 0;
+  if (lane < K) {
+    const int64_t slot = bin * K + lane;
+    coff = p.sl.coff[slot];
+    voff = p.sl.voff[slot];
+    len = p.sl.len[slot];
+    row = p.sl.row[slot];
+    if (p.n_seg > 1 && c_begin > 0) {   // first stored column >= c_begin (rows are ascending)
+      int lo = 0, hi = len;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)p.cols[coff + mid] - p.col_base < c_begin) lo = mid + 1; else hi = mid;
+      }
+      pos = lo;
+    }
+    if (pos < len) next_col = p.cols[coff + pos] - p.col_base;
+  }
+  float acc[K][4 * NV];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int e = 0; e < 4 * NV; ++e) acc[k][e] = 0.f;
+  const uint32_t scr = smem_u32(scratch + warp * 32);
+  const bool atomic = p.n_seg > 1;
+  bool violation = false;
+  // byte offset of this lane's q-th float4 inside a density row; lanes past the row end re-read its
+  // last float4 (a broadcast, no extra wavefront) into accumulators that are never flushed
+  const int nq = ldD >> 2;
+  uint32_t lane_off[NV];
+#pragma unroll
+  for (int q = 0; q < NV; ++q) lane_off[q] = (uint32_t)hs_min(lane + 32 * q, nq - 1) * 16u;
+  constexpr int GROUP = NV == 1 ? 4 : (NV == 2 ? 2 : 1);   // non-zeros whose loads are issued together
+  const unsigned row_bytes = (unsigned)ldD * 4u;
+
+  for (int s = 0; s < n_slabs; ++s) {
+    const int b = s & 1;
+    const int64_t cbase64 = c_begin + (int64_t)s * S;
+    const int cbase = (int)cbase64;
+    const int cend = (int)hs_min<int64_t>(c_end, cbase64 + S);
+    const unsigned act = __ballot_sync(0xffffffffu, lane < K && next_col < cend);
+    // software prefetch: the batch of (col, val) the next visit starts with is always in flight
+    int pf_c = 0;
+    float pf_v = 0.f;
+    if (act) {
+      const int k0 = __ffs(act) - 1;
+      const int64_t co = __shfl_sync(0xffffffffu, coff, k0), vo = __shfl_sync(0xffffffffu, voff, k0);
+      const int idx = __shfl_sync(0xffffffffu, pos, k0) + lane;
+      if (idx < __shfl_sync(0xffffffffu, len, k0)) {
+        pf_c = __ldg(p.cols + co + idx);
+        pf_v = __ldg(p.vals + vo + idx);
+      }
+    }
+    if (warp == 0) {
+      produce(s + 1, true);     // the slab this iteration reads must have been requested
+      produce(s + 2, false);    // the next one as soon as its buffer is free
+    }
+    // Every warp observes every fill, active rows or not: a warp that ran ahead of the data could
+    // otherwise lap the two-phase parity of the barriers (and release a buffer twice in one phase).
+    mbar_wait(full0 + 8 * b, (s >> 1) & 1);
+    if (act) {
+      const uint32_t slab = smem_u32(slab0) + (uint32_t)(b * slab_bytes);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if ((act >> k) & 1u) {
+          const int64_t co = __shfl_sync(0xffffffffu, coff, k);
+          const int64_t vo = __shfl_sync(0xffffffffu, voff, k);
+          const int len_k = __shfl_sync(0xffffffffu, len, k);
+          int pos_k = __shfl_sync(0xffffffffu, pos, k);
+          const unsigned rest = (k + 1 < 32) ? (act >> (k + 1)) : 0u;
+          int nc = 0x7fffffff, visited = 0;
+          for (;;) {
+            const int idx = pos_k + lane;
+            const int mc = idx < len_k ? pf_c - p.col_base : 0x7fffffff;
+            const float mv = pf_v;
+            const unsigned in = __ballot_sync(0xffffffffu, mc < cend);
+            const int n_in = __popc(in);
+            // next batch: more of this row, or the first batch of the next active row of this slab
+            if (n_in == 32) {
+              if (idx + 32 < len_k) {
+                pf_c = __ldg(p.cols + co + idx + 32);
+                pf_v = __ldg(p.vals + vo + idx + 32);
+              }
+            } else if (rest) {
+              const int k2 = k + __ffs(rest);
+              const int64_t co2 = __shfl_sync(0xffffffffu, coff, k2), vo2 = __shfl_sync(0xffffffffu, voff, k2);
+              const int idx2 = __shfl_sync(0xffffffffu, pos, k2) + lane;
+              if (idx2 < __shfl_sync(0xffffffffu, len, k2)) {
+                pf_c = __ldg(p.cols + co2 + idx2);
+                pf_v = __ldg(p.vals + vo2 + idx2);
+              }
+            }
+            // entries of this slab must form a prefix of the batch and none may lie before the slab
+            if (mc < cbase || in != (n_in == 32 ? 0xffffffffu : ((1u << n_in) - 1u))) violation = true;
+            const bool here = mc >= cbase && mc < cend;   // anything else must never index the slab
+            sts_u2(scr + lane * 8, here ? (unsigned)(mc - cbase) * row_bytes : 0u, here ? __float_as_uint(mv) : 0u);
+            __syncwarp();
+            float part[4 * NV];
+#pragma unroll
+            for (int e = 0; e < 4 * NV; ++e) part[e] = 0.f;
+            int t = 0;
+            for (; t + GROUP <= n_in; t += GROUP) {
+              uint32_t eo[GROUP];
+              float ev[GROUP];
+              if (GROUP == 4) {
+                const uint4 e01 = lds_u4(scr + t * 8), e23 = lds_u4(scr + t * 8 + 16);
+                eo[0] = e01.x; ev[0] = __uint_as_float(e01.y); eo[1 % GROUP] = e01.z; ev[1 % GROUP] = __uint_as_float(e01.w);
+                eo[2 % GROUP] = e23.x; ev[2 % GROUP] = __uint_as_float(e23.y); eo[3 % GROUP] = e23.z; ev[3 % GROUP] = __uint_as_float(e23.w);
+              } else if (GROUP == 2) {
+                const uint4 e01 = lds_u4(scr + t * 8);
+                eo[0] = e01.x; ev[0] = __uint_as_float(e01.y); eo[1 % GROUP] = e01.z; ev[1 % GROUP] = __uint_as_float(e01.w);
+              } else {
+                const uint2 e0 = lds_u2(scr + t * 8);
+                eo[0] = e0.x; ev[0] = __uint_as_float(e0.y);
+              }
+              float4 d[GROUP][NV];
+#pragma unroll
+              for (int i = 0; i < GROUP; ++i)
+#pragma unroll
+                for (int q = 0; q < NV; ++q) d[i][q] = lds_f4(slab + eo[i] + lane_off[q]);
+#pragma unroll
+              for (int i = 0; i < GROUP; ++i)
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                  part[4 * q + 0] = fmaf(ev[i], d[i][q].x, part[4 * q + 0]);
+                  part[4 * q + 1] = fmaf(ev[i], d[i][q].y, part[4 * q + 1]);
+                  part[4 * q + 2] = fmaf(ev[i], d[i][q].z, part[4 * q + 2]);
+                  part[4 * q + 3] = fmaf(ev[i], d[i][q].w, part[4 * q + 3]);
+                }
+            }
+            for (; t < n_in; ++t) {
+              const uint2 e0 = lds_u2(scr + t * 8);
+              const float v = __uint_as_float(e0.y);
+#pragma unroll
+              for (int q = 0; q < NV; ++q) {
+                const float4 dd = lds_f4(slab + e0.x + lane_off[q]);
+                part[4 * q + 0] = fmaf(v, dd.x, part[4 * q + 0]);
+                part[4 * q + 1] = fmaf(v, dd.y, part[4 * q + 1]);
+                part[4 * q + 2] = fmaf(v, dd.z, part[4 * q + 2]);
+                part[4 * q + 3] = fmaf(v, dd.w, part[4 * q + 3]);
+              }
+            }
+            // two-level fp32: at most 32 products per partial, at most kFlushNnz/32 partials per flush
+#pragma unroll
+            for (int e = 0; e < 4 * NV; ++e) acc[k][e] += part[e];
+            __syncwarp();
+            pos_k += n_in;
+            visited += n_in;
+            if (n_in < 32) {
+              nc = __shfl_sync(0xffffffffu, mc, n_in);
+              break;
+            }
+          }
+          if (lane == k) {
+            pos = pos_k;
+            next_col = nc;
+            cnt += visited;
+          }
+          if (warp == 0) produce(s + 2, false);
+        }
+      }
+      // fp32 -> fp64 for the rows that have accumulated enough products
+      const unsigned fm = __ballot_sync(0xffffffffu, lane < K && cnt >= kFlushNnz);
+      if (fm) {
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          if ((fm >> k) & 1u) {
+            const int row_k = __shfl_sync(0xffffffffu, row, k);
+            flush_row<NV, K>(acc[k], p.P64 + (int64_t)row_k * p.ldP, lane, ldD, atomic);
+          }
+        if ((fm >> lane) & 1u) cnt = 0;
+      }
+    }
+    // this warp is done with buffer b (whether or not it touched it)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * b);
+  }
+
+  // no copy may be in flight when the CTA retires
+  if (warp == 0)
+    for (int s = hs_max(0, n_slabs - 2); s < n_slabs; ++s) mbar_wait(full0 + 8 * (s & 1), (s >> 1) & 1);
+
+  // ---------------- final flush, left-over (out of range) ids ----------------
+  const unsigned fm = __ballot_sync(0xffffffffu, lane < K && row >= 0 && cnt > 0);
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+    if ((fm >> k) & 1u) {
+      const int row_k = __shfl_sync(0xffffffffu, row, k);
+      flush_row<NV, K>(acc[k], p.P64 + (int64_t)row_k * p.ldP, lane, ldD, atomic);
+    }
+  // ids >= N are never consumed: poison the row like the gather kernel does (last segment only)
+  if (lane < K && row >= 0 && blockIdx.y == gridDim.y - 1 && pos < len) p.P64[(int64_t)row * p.ldP] = NAN;
+  if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(p.flags, 1);
+}
+
+// ---- KL epilogue over the fp64 column sums -----------------------------------------------------
+template <int NACC>
+__global__ void __launch_bounds__(256)
+k_p64_epilogue(const double* __restrict__ P64, int64_t n_rows, int ldP, int G, const double* __restrict__ Q,
+               int n_perm, int64_t n_sel, const int* __restrict__ flags, double* __restrict__ out) {
+  if (*flags & 1) return;   // the fallback kernel produces the output
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  double pr[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const int j = lane + 32 * a;
+    pr[a] = j < G ? P64[row * ldP + j] : 0.0;
+  }
+  const double kl = hs_kl_epilogue<NACC>(pr, Q, G, lane);
+  if (lane == 0) {
+    int64_t o = row;
+    if (n_perm > 0) {
+      const int64_t s = row / n_perm, r = row - s * n_perm;
+      o = s + r * n_sel;
+    }
+    out[o] = kl;
+  }
+}
+
+template <int NV, int K, int W>
+int launch_spmm(hs_ctx* ctx, const SpmmParams& prm, int n_tiles, size_t smem) {
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_slab_spmm<NV, K, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(n_tiles, prm.n_seg);
+  k_slab_spmm<NV, K, W><<<grid, W * 32, smem, ctx->stream>>>(prm);
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
+
+// Tile shapes (rows per warp K, warps per CTA W) per float4-per-lane count NV, smallest first.
+// 4*NV*K accumulator registers per thread: W = 16 allows 128 registers, W = 12 allows 168.
+struct Shape { int k, w; };
+const Shape kShapes1[] = {{1, 16}, {2, 16}, {4, 16}, {8, 16}, {17, 12}};
+const Shape kShapes2[] = {{1, 16}, {2, 16}, {4, 16}, {8, 12}};
+const Shape kShapes4[] = {{1, 16}, {2, 16}, {4, 12}};
+const Shape kShapes8[] = {{1, 16}, {2, 12}};
+
+// smallest shape whose single wave of `sms` CTAs covers n_rows; the largest one otherwise
+Shape pick_shape(int nv, int64_t n_rows, int sms) {
+  const Shape* t = nv == 1 ? kShapes1 : nv == 2 ? kShapes2 : nv == 4 ? kShapes4 : kShapes8;
+  const int n = nv == 1 ? 5 : nv == 2 ? 4 : nv == 4 ? 3 : 2;
+  for (int i = 0; i < n; ++i)
+    if ((int64_t)t[i].k * t[i].w * sms >= n_rows) return t[i];
+  return t[n - 1];
+}
+
+}  // namespace
+
+// Sparse rows x resident density matrix -> D_KL.  PERM selects the randomization layout (see k_row_len).
+// out_dev: fp64, n_rows entries (CSR) or n_sel x n_perm column-major (PERM).
+// flag_dev_out (optional) receives the device address of the violation flag so that the caller can
+// chain the order-independent fallback without a host round trip.
+int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
+                     const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
+                     const int** flag_dev_out) {
+  const int64_t n_rows = perm ? n_units * (int64_t)n_perm : n_units;
+  if (n_rows <= 0) return HS_OK;
+  if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many rows (%lld) for one call", (long long)n_rows);
+  const int G = ctx->G, ldD = ctx->ldD;
+  const int nvq = (ldD / 4 + 31) / 32;                      // float4 per lane
+  const int NV = nvq <= 1 ? 1 : nvq <= 2 ? 2 : nvq <= 4 ? 4 : 8;
+  if (nvq > 8) return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d exceeds the supported maximum of 1024", G);
+  const int sms = ctx->sm_count;
+  const Shape shp = pick_shape(NV, n_rows, sms);
+  const int K = shp.k, kWarps = shp.w;
+  const int n_tiles = (int)((n_rows + (int64_t)kWarps * K - 1) / ((int64_t)kWarps * K));
+  const int n_bins = n_tiles * kWarps;
+  const int64_t n_slots = (int64_t)n_bins * K;
+
+  // slab size: two buffers + scratch + barriers within the opt-in shared memory limit
+  const size_t fixed = kMaxWarps * 32 * sizeof(uint2) + 64;
+  int S = (int)((kMaxSmem - fixed) / (2 * (size_t)ldD * sizeof(float)));
+  S = hs_min<int>(S & ~3, 2048);
+  if (S < 4) return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d leaves no room for a density slab", G);
+  if ((int64_t)S > ctx->N) S = (int)((ctx->N + 3) & ~3LL);
+  const size_t smem = 2 * (size_t)S * ldD * sizeof(float) + fixed;
+  // split the cell axis over grid.y when there are too few row tiles to fill the machine
+  int n_seg = 1;
+  const int64_t total_slabs = (ctx->N + S - 1) / S;
+  if (n_tiles * 2 <= sms) n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms / n_tiles, total_slabs / 4));
+  const int64_t seg_cells = ((total_slabs + n_seg - 1) / n_seg) * S;
+  n_seg = (int)((ctx->N + seg_cells - 1) / seg_cells);
+
+  // ---- scratch ----
+  const int ldP = ldD;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                            (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows, 0, 32, ctx->stream);
+  const size_t keys_b = ((size_t)n_rows * 4 + 255) & ~(size_t)255;
+  const size_t slots_b = ((size_t)n_slots * 8 + 255) & ~(size_t)255;
+  const size_t slots4_b = ((size_t)n_slots * 4 + 255) & ~(size_t)255;
+  const size_t need = 256 + 4 * keys_b + 2 * slots_b + 2 * slots4_b + ((cub_bytes + 255) & ~(size_t)255);
+  HS_TRY(hs_ensure(ctx, ctx->spmm_ws, need));
+  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_rows * ldP));
+  char* w = (char*)ctx->spmm_ws.p;
+  int* flags = (int*)w;                    w += 256;
+  uint32_t* keys_in = (uint32_t*)w;        w += keys_b;
+  uint32_t* keys_out = (uint32_t*)w;       w += keys_b;
+  int32_t* rows_in = (int32_t*)w;          w += keys_b;
+  int32_t* rows_out = (int32_t*)w;         w += keys_b;
+  Slots sl;
+  sl.coff = (int64_t*)w;                   w += slots_b;
+  sl.voff = (int64_t*)w;                   w += slots_b;
+  sl.len = (int32_t*)w;                    w += slots4_b;
+  sl.row = (int32_t*)w;                    w += slots4_b;
+  void* cub_ws = w;
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemsetAsync(flags, 0, 256, st));
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_rows * ldP, st));
+
+  const int tb = 256;
+  if (perm)
+    k_row_len<true><<<(unsigned)((n_rows + tb - 1) / tb), tb, 0, st>>>(ptr_dev, n_rows, n_perm, keys_in, rows_in, flags);
+  else
+    k_row_len<false><<<(unsigned)((n_rows + tb - 1) / tb), tb, 0, st>>>(ptr_dev, n_rows, n_perm, keys_in, rows_in, flags);
+  HS_LAUNCH_CHECK(ctx);
+  HS_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(cub_ws, cub_bytes, keys_in, keys_out, rows_in, rows_out,
+                                                         (int)n_rows, 0, 32, st));
+  ctx->launches += 3;   // cub: histogram + onesweep passes (counted once as a family)
+  if (perm)
+    k_build_slots<true><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out, n_rows, n_perm, n_bins, K, sl);
+  else
+    k_build_slots<false><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out, n_rows, n_perm, n_bins, K, sl);
+  HS_LAUNCH_CHECK(ctx);
+
+  SpmmParams prm;
+  prm.sl = sl;
+  prm.cols = cols_dev;
+  prm.vals = vals_dev;
+  prm.col_base = col_base;
+  prm.D = (const float*)ctx->D32.p;
+  prm.ldD = ldD;
+  prm.N = ctx->N;
+  prm.slab_cells = S;
+  prm.seg_cells = seg_cells;
+  prm.n_seg = n_seg;
+  prm.P64 = (double*)ctx->part.p;
+  prm.ldP = ldP;
+  prm.flags = flags;
+
+#define HS_SPMM_CASE(NVv, Kv, Wv) \
+  if (NV == NVv && K == Kv && kWarps == Wv) { HS_TRY((launch_spmm<NVv, Kv, Wv>(ctx, prm, n_tiles, smem))); } else
+  HS_SPMM_CASE(1, 1, 16) HS_SPMM_CASE(1, 2, 16) HS_SPMM_CASE(1, 4, 16) HS_SPMM_CASE(1, 8, 16) HS_SPMM_CASE(1, 17, 12)
+  HS_SPMM_CASE(2, 1, 16) HS_SPMM_CASE(2, 2, 16) HS_SPMM_CASE(2, 4, 16) HS_SPMM_CASE(2, 8, 12)
+  HS_SPMM_CASE(4, 1, 16) HS_SPMM_CASE(4, 2, 16) HS_SPMM_CASE(4, 4, 12)
+  HS_SPMM_CASE(8, 1, 16) HS_SPMM_CASE(8, 2, 12)
+  { return hs_fail(ctx, HS_ERR_INVALID, "internal: no slab kernel for NV=%d K=%d W=%d", NV, K, kWarps); }
+#undef HS_SPMM_CASE
+
+  const int nacc = (G + 31) / 32;
+  const unsigned eb = (unsigned)((n_rows + 7) / 8);
+  const double* Q = (const double*)ctx->Q.p;
+  const int np = perm ? n_perm : 0;
+#define HS_EPI(NA) k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_rows, ldP, G, Q, np, n_units, flags, out_dev)
+  if (nacc <= 1) HS_EPI(1);
+  else if (nacc <= 2) HS_EPI(2);
+  else if (nacc <= 3) HS_EPI(3);
+  else if (nacc <= 4) HS_EPI(4);
+  else if (nacc <= 8) HS_EPI(8);
+  else if (nacc <= 16) HS_EPI(16);
+  else HS_EPI(32);
+#undef HS_EPI
+  HS_LAUNCH_CHECK(ctx);
+  if (flag_dev_out) *flag_dev_out = flags;
+  return HS_OK;
+}

@@ -85,9 +85,13 @@ class DeviceContext:
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._lib.hs_set_stream(self._h, C.c_void_p(cuda_stream_ptr or None)), "hs_set_stream")
 
-    def use_torch_stream(self):
+    def use_torch_stream(self, stream=None):
+        """Run the library's kernels on a torch stream (default: torch's current stream), so that
+        torch.cuda.Event timings bracket them.  torch's default stream is the legacy NULL stream,
+        which the C ABI spells cudaStreamLegacy (NULL means "the context's own stream")."""
         import torch
-        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self.set_stream(s.cuda_stream or 0x1)
 
     def synchronize(self):
         self._check(self._lib.hs_synchronize(self._h), "hs_synchronize")

@@ -109,4 +109,18 @@ def test_edge_rows(ctx, toy):
     want = ho.dkl_observed(sp, ref["density"], ref["Q"])
     assert _rel(got[:4], want) < RTOL_DKL
     assert np.isnan(got[4])
+    # ascending rows (the slab kernel keeps them): an id >= n_cells poisons only its own row
+    p2 = np.array([0, 2, 4, 4, 7], dtype=np.int64)
+    j2 = np.array([3, 599, 10, 601, 0, 1, 600], dtype=np.int32)
+    x2 = np.array([1.0, 2.0, 3.0, 4.0, 0.5, 0.25, 2.0])
+    got2 = ctx.dkl_csr(p2, j2, x2)
+    sp2 = ho.RowSparse(p=np.array([0, 2, 2, 2, 5]), j=np.array([3, 599, 0, 1, 600], np.int32),
+                       x=np.array([1.0, 2.0, 0.5, 0.25, 2.0]), shape=(4, 601))
+    want2 = ho.dkl_observed(sp2, ref["density"], ref["Q"])
+    assert _rel(got2[[0, 3]], want2[[0, 3]]) < RTOL_DKL
+    assert np.isnan(got2[1])
+    assert abs(got2[2] - want2[2]) < 1e-9          # empty row: P = pseudo everywhere, as the reference
+    # a negative id cannot be dereferenced either
+    got3 = ctx.dkl_csr(np.array([0, 2, 3], dtype=np.int64), np.array([-1, 5, 9], np.int32), np.array([1.0, 1.0, 1.0]))
+    assert np.isnan(got3[0]) and np.isfinite(got3[1])
     assert ctx.dkl_csr(np.array([0], dtype=np.int64), np.zeros(0, np.int32), np.zeros(0)).shape == (0,)
