@@ -509,6 +509,7 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     xs_h = torch.from_numpy(np.ascontiguousarray(xs.T)).pin_memory()       # column-major N x d
     grid_h = torch.from_numpy(np.ascontiguousarray(grid.T)).pin_memory()
     torch.cuda.synchronize()
+    torch.cuda.empty_cache()        # the library allocates its upload buffers with cudaMalloc
     p_np, j_np, x_np = p_h.numpy(), j_h.numpy(), x_h.numpy()
     out_rand = np.empty((max(n_sel_local, 1), r_loc), dtype=np.float64, order="F")
 

@@ -158,7 +158,7 @@ void hs_destroy(hs_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->D32, &ctx->Q, &ctx->sq, &ctx->rowmin, &ctx->nearest, &ctx->sel, &ctx->qpart,
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
-                    &ctx->ptrs, &ctx->dense_in, &ctx->spmm_ws, &ctx->cols32};
+                    &ctx->ptrs, &ctx->dense_in, &ctx->spmm_ws, &ctx->cols32, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -368,7 +368,7 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
 
   ScopedTimer tm(ctx, timer_slot);
   if (perm)
-    HS_TRY(hs_run_perm_csr(ctx, (const int64_t*)ctx->ptrs.p, n_units, (const float*)ctx->vals32.p,
+    HS_TRY(hs_run_perm_csr(ctx, (const int64_t*)ctx->ptrs.p, n_units, n_vals, (const float*)ctx->vals32.p,
                            (const int32_t*)ctx->cols32.p, n_perm, index_base, dev_out));
   else
     HS_TRY(hs_run_csr(ctx, (const int64_t*)ctx->ptrs.p, (const int32_t*)ctx->cols32.p, (const float*)ctx->vals32.p,
@@ -388,9 +388,10 @@ static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_
   size_t free_b = 0, total_b = 0;
   HS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   // bytes already held by the grow-only upload buffers count as available
-  free_b += ctx->cols32.cap + ctx->vals32.cap;
+  free_b += ctx->cols32.cap + ctx->vals32.cap + ctx->perm_cols.cap + ctx->perm_vals.cap;
   const double budget = (double)env_size("HS_UPLOAD_BUDGET", (size_t)(0.80 * (double)free_b));
-  const double bytes_per_value = 4.0 * (double)ipv + 4.0;
+  // uploaded ids + fp32 values (+ the slab-bucketed copy of both for the permutation form)
+  const double bytes_per_value = 4.0 * (double)ipv + 4.0 + (perm ? 8.0 * (double)ipv : 0.0);
   std::vector<double> tmp;
   cudaStream_t st = ctx->stream;
   int64_t ub = 0;
@@ -511,8 +512,13 @@ int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
   HS_TRY(set_device(ctx));
   if (n_sel < 0 || n_perm <= 0 || !gene_ptr_dev || !out_dev)
     return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_dev: bad arguments");
+  if (n_sel == 0) return HS_OK;
+  int64_t n_vals = 0;   // the slab bucketing sizes its buffers from the total number of stored values
+  HS_CUDA(ctx, cudaMemcpyAsync(&n_vals, gene_ptr_dev + n_sel, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_vals < 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_dev: gene_ptr is not a prefix sum");
   ScopedTimer tm(ctx, HS_T_PERM);
-  HS_TRY(hs_run_perm_csr(ctx, gene_ptr_dev, n_sel, val_dev, ind_dev, n_perm, index_base, out_dev));
+  HS_TRY(hs_run_perm_csr(ctx, gene_ptr_dev, n_sel, n_vals, val_dev, ind_dev, n_perm, index_base, out_dev));
   tm.stop();
   return HS_OK;
 }

@@ -62,6 +62,7 @@ struct hs_ctx {
   DevBuf dense_in;  // uploaded dense expression (fp64 col-major)
   DevBuf spmm_ws;   // slab kernel: flags, sort keys, slot table, cub workspace
   DevBuf cols32;    // uploaded column / cell ids (host-pointer entry points)
+  DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, slab-bucketed ids / values
   void* pinned = nullptr;      // small pinned host bounce buffer
   size_t pinned_cap = 0;
 };
@@ -101,11 +102,13 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
 // slab-staged sparse contraction (hs_spmm.cu); see there for the arguments
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     const int** flag_dev_out);
+                     int out_n_perm, int64_t out_n_sel, const int** flag_dev_out);
+int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
+                       const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,
                int64_t n_rows, double* out_dev);
-int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
-                    const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
+int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
+                    const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_dense_f64(hs_ctx* ctx, const double* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,

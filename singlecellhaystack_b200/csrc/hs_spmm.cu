@@ -265,6 +265,25 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
     for (int e = 0; e < 4 * NV; ++e) acc[k][e] = 0.f;
   const uint32_t scr = smem_u32(scratch + warp * 32);
   const bool atomic = p.n_seg > 1;
+  // move the fp32 sums of the rows in `mask` into the fp64 column sums (one copy of the code)
+  auto flush_rows = [&](unsigned mask) {
+    while (mask) {
+      const int k = __ffs(mask) - 1;
+      mask &= mask - 1;
+      float tmp[4 * NV];
+#pragma unroll
+      for (int kk = 0; kk < K; ++kk)
+        if (kk == k) {
+#pragma unroll
+          for (int e = 0; e < 4 * NV; ++e) {
+            tmp[e] = acc[kk][e];
+            acc[kk][e] = 0.f;
+          }
+        }
+      const int row_k = __shfl_sync(0xffffffffu, row, k);
+      flush_row<NV, K>(tmp, p.P64 + (int64_t)row_k * p.ldP, lane, ldD, atomic);
+    }
+  };
   bool violation = false;
   // byte offset of this lane's q-th float4 inside a density row; lanes past the row end re-read its
   // last float4 (a broadcast, no extra wavefront) into accumulators that are never flushed
@@ -302,114 +321,119 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
     mbar_wait(full0 + 8 * b, (s >> 1) & 1);
     if (act) {
       const uint32_t slab = smem_u32(slab0) + (uint32_t)(b * slab_bytes);
+      // One copy of the visit code for all rows (a K-fold unrolled copy overflows the instruction
+      // cache: warps sit in different rows); only the register accumulators need a static index.
+      unsigned todo = act;
+      while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t co = __shfl_sync(0xffffffffu, coff, k);
+        const int64_t vo = __shfl_sync(0xffffffffu, voff, k);
+        const int len_k = __shfl_sync(0xffffffffu, len, k);
+        int pos_k = __shfl_sync(0xffffffffu, pos, k);
+        int nc = 0x7fffffff, visited = 0;
+        float vis[4 * NV];            // this visit's products (fp32, two levels: <= 32 per partial)
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        if ((act >> k) & 1u) {
-          const int64_t co = __shfl_sync(0xffffffffu, coff, k);
-          const int64_t vo = __shfl_sync(0xffffffffu, voff, k);
-          const int len_k = __shfl_sync(0xffffffffu, len, k);
-          int pos_k = __shfl_sync(0xffffffffu, pos, k);
-          const unsigned rest = (k + 1 < 32) ? (act >> (k + 1)) : 0u;
-          int nc = 0x7fffffff, visited = 0;
-          for (;;) {
-            const int idx = pos_k + lane;
-            const int mc = idx < len_k ? pf_c - p.col_base : 0x7fffffff;
-            const float mv = pf_v;
-            const unsigned in = __ballot_sync(0xffffffffu, mc < cend);
-            const int n_in = __popc(in);
-            // next batch: more of this row, or the first batch of the next active row of this slab
-            if (n_in == 32) {
-              if (idx + 32 < len_k) {
-                pf_c = __ldg(p.cols + co + idx + 32);
-                pf_v = __ldg(p.vals + vo + idx + 32);
-              }
-            } else if (rest) {
-              const int k2 = k + __ffs(rest);
-              const int64_t co2 = __shfl_sync(0xffffffffu, coff, k2), vo2 = __shfl_sync(0xffffffffu, voff, k2);
-              const int idx2 = __shfl_sync(0xffffffffu, pos, k2) + lane;
-              if (idx2 < __shfl_sync(0xffffffffu, len, k2)) {
-                pf_c = __ldg(p.cols + co2 + idx2);
-                pf_v = __ldg(p.vals + vo2 + idx2);
-              }
+        for (int e = 0; e < 4 * NV; ++e) vis[e] = 0.f;
+        for (;;) {
+          const int idx = pos_k + lane;
+          const int mc = idx < len_k ? pf_c - p.col_base : 0x7fffffff;
+          const float mv = pf_v;
+          const unsigned in = __ballot_sync(0xffffffffu, mc < cend);
+          const int n_in = __popc(in);
+          // next batch: more of this row, or the first batch of the next active row of this slab
+          if (n_in == 32) {
+            if (idx + 32 < len_k) {
+              pf_c = __ldg(p.cols + co + idx + 32);
+              pf_v = __ldg(p.vals + vo + idx + 32);
             }
-            // entries of this slab must form a prefix of the batch and none may lie before the slab
-            if (mc < cbase || in != (n_in == 32 ? 0xffffffffu : ((1u << n_in) - 1u))) violation = true;
-            const bool here = mc >= cbase && mc < cend;   // anything else must never index the slab
-            sts_u2(scr + lane * 8, here ? (unsigned)(mc - cbase) * row_bytes : 0u, here ? __float_as_uint(mv) : 0u);
-            __syncwarp();
-            float part[4 * NV];
-#pragma unroll
-            for (int e = 0; e < 4 * NV; ++e) part[e] = 0.f;
-            int t = 0;
-            for (; t + GROUP <= n_in; t += GROUP) {
-              uint32_t eo[GROUP];
-              float ev[GROUP];
-              if (GROUP == 4) {
-                const uint4 e01 = lds_u4(scr + t * 8), e23 = lds_u4(scr + t * 8 + 16);
-                eo[0] = e01.x; ev[0] = __uint_as_float(e01.y); eo[1 % GROUP] = e01.z; ev[1 % GROUP] = __uint_as_float(e01.w);
-                eo[2 % GROUP] = e23.x; ev[2 % GROUP] = __uint_as_float(e23.y); eo[3 % GROUP] = e23.z; ev[3 % GROUP] = __uint_as_float(e23.w);
-              } else if (GROUP == 2) {
-                const uint4 e01 = lds_u4(scr + t * 8);
-                eo[0] = e01.x; ev[0] = __uint_as_float(e01.y); eo[1 % GROUP] = e01.z; ev[1 % GROUP] = __uint_as_float(e01.w);
-              } else {
-                const uint2 e0 = lds_u2(scr + t * 8);
-                eo[0] = e0.x; ev[0] = __uint_as_float(e0.y);
-              }
-              float4 d[GROUP][NV];
-#pragma unroll
-              for (int i = 0; i < GROUP; ++i)
-#pragma unroll
-                for (int q = 0; q < NV; ++q) d[i][q] = lds_f4(slab + eo[i] + lane_off[q]);
-#pragma unroll
-              for (int i = 0; i < GROUP; ++i)
-#pragma unroll
-                for (int q = 0; q < NV; ++q) {
-                  part[4 * q + 0] = fmaf(ev[i], d[i][q].x, part[4 * q + 0]);
-                  part[4 * q + 1] = fmaf(ev[i], d[i][q].y, part[4 * q + 1]);
-                  part[4 * q + 2] = fmaf(ev[i], d[i][q].z, part[4 * q + 2]);
-                  part[4 * q + 3] = fmaf(ev[i], d[i][q].w, part[4 * q + 3]);
-                }
+          } else if (todo) {
+            const int k2 = __ffs(todo) - 1;
+            const int64_t co2 = __shfl_sync(0xffffffffu, coff, k2), vo2 = __shfl_sync(0xffffffffu, voff, k2);
+            const int idx2 = __shfl_sync(0xffffffffu, pos, k2) + lane;
+            if (idx2 < __shfl_sync(0xffffffffu, len, k2)) {
+              pf_c = __ldg(p.cols + co2 + idx2);
+              pf_v = __ldg(p.vals + vo2 + idx2);
             }
-            for (; t < n_in; ++t) {
+          }
+          // entries of this slab must form a prefix of the batch and none may lie before the slab
+          if (mc < cbase || in != (n_in == 32 ? 0xffffffffu : ((1u << n_in) - 1u))) violation = true;
+          const bool here = mc >= cbase && mc < cend;   // anything else must never index the slab
+          sts_u2(scr + lane * 8, here ? (unsigned)(mc - cbase) * row_bytes : 0u, here ? __float_as_uint(mv) : 0u);
+          __syncwarp();
+          float part[4 * NV];
+#pragma unroll
+          for (int e = 0; e < 4 * NV; ++e) part[e] = 0.f;
+          int t = 0;
+          for (; t + GROUP <= n_in; t += GROUP) {
+            uint32_t eo[GROUP];
+            float ev[GROUP];
+            if (GROUP == 4) {
+              const uint4 e01 = lds_u4(scr + t * 8), e23 = lds_u4(scr + t * 8 + 16);
+              eo[0] = e01.x; ev[0] = __uint_as_float(e01.y); eo[1 % GROUP] = e01.z; ev[1 % GROUP] = __uint_as_float(e01.w);
+              eo[2 % GROUP] = e23.x; ev[2 % GROUP] = __uint_as_float(e23.y); eo[3 % GROUP] = e23.z; ev[3 % GROUP] = __uint_as_float(e23.w);
+            } else if (GROUP == 2) {
+              const uint4 e01 = lds_u4(scr + t * 8);
+              eo[0] = e01.x; ev[0] = __uint_as_float(e01.y); eo[1 % GROUP] = e01.z; ev[1 % GROUP] = __uint_as_float(e01.w);
+            } else {
               const uint2 e0 = lds_u2(scr + t * 8);
-              const float v = __uint_as_float(e0.y);
+              eo[0] = e0.x; ev[0] = __uint_as_float(e0.y);
+            }
+            float4 d[GROUP][NV];
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i)
+#pragma unroll
+              for (int q = 0; q < NV; ++q) d[i][q] = lds_f4(slab + eo[i] + lane_off[q]);
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i)
 #pragma unroll
               for (int q = 0; q < NV; ++q) {
-                const float4 dd = lds_f4(slab + e0.x + lane_off[q]);
-                part[4 * q + 0] = fmaf(v, dd.x, part[4 * q + 0]);
-                part[4 * q + 1] = fmaf(v, dd.y, part[4 * q + 1]);
-                part[4 * q + 2] = fmaf(v, dd.z, part[4 * q + 2]);
-                part[4 * q + 3] = fmaf(v, dd.w, part[4 * q + 3]);
+                part[4 * q + 0] = fmaf(ev[i], d[i][q].x, part[4 * q + 0]);
+                part[4 * q + 1] = fmaf(ev[i], d[i][q].y, part[4 * q + 1]);
+                part[4 * q + 2] = fmaf(ev[i], d[i][q].z, part[4 * q + 2]);
+                part[4 * q + 3] = fmaf(ev[i], d[i][q].w, part[4 * q + 3]);
               }
-            }
-            // two-level fp32: at most 32 products per partial, at most kFlushNnz/32 partials per flush
+          }
+          for (; t < n_in; ++t) {
+            const uint2 e0 = lds_u2(scr + t * 8);
+            const float v = __uint_as_float(e0.y);
 #pragma unroll
-            for (int e = 0; e < 4 * NV; ++e) acc[k][e] += part[e];
-            __syncwarp();
-            pos_k += n_in;
-            visited += n_in;
-            if (n_in < 32) {
-              nc = __shfl_sync(0xffffffffu, mc, n_in);
-              break;
+            for (int q = 0; q < NV; ++q) {
+              const float4 dd = lds_f4(slab + e0.x + lane_off[q]);
+              part[4 * q + 0] = fmaf(v, dd.x, part[4 * q + 0]);
+              part[4 * q + 1] = fmaf(v, dd.y, part[4 * q + 1]);
+              part[4 * q + 2] = fmaf(v, dd.z, part[4 * q + 2]);
+              part[4 * q + 3] = fmaf(v, dd.w, part[4 * q + 3]);
             }
           }
-          if (lane == k) {
-            pos = pos_k;
-            next_col = nc;
-            cnt += visited;
+#pragma unroll
+          for (int e = 0; e < 4 * NV; ++e) vis[e] += part[e];
+          __syncwarp();
+          pos_k += n_in;
+          visited += n_in;
+          if (n_in < 32) {
+            nc = __shfl_sync(0xffffffffu, mc, n_in);
+            break;
           }
-          if (warp == 0) produce(s + 2, false);
         }
+        // fold the visit into the row's register accumulators (static register index per case)
+#pragma unroll
+        for (int kk = 0; kk < K; ++kk)
+          if (kk == k) {
+#pragma unroll
+            for (int e = 0; e < 4 * NV; ++e) acc[kk][e] += vis[e];
+          }
+        if (lane == k) {
+          pos = pos_k;
+          next_col = nc;
+          cnt += visited;
+        }
+        if (warp == 0) produce(s + 2, false);
       }
       // fp32 -> fp64 for the rows that have accumulated enough products
       const unsigned fm = __ballot_sync(0xffffffffu, lane < K && cnt >= kFlushNnz);
       if (fm) {
-#pragma unroll
-        for (int k = 0; k < K; ++k)
-          if ((fm >> k) & 1u) {
-            const int row_k = __shfl_sync(0xffffffffu, row, k);
-            flush_row<NV, K>(acc[k], p.P64 + (int64_t)row_k * p.ldP, lane, ldD, atomic);
-          }
+        flush_rows(fm);
         if ((fm >> lane) & 1u) cnt = 0;
       }
     }
@@ -423,13 +447,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
     for (int s = hs_max(0, n_slabs - 2); s < n_slabs; ++s) mbar_wait(full0 + 8 * (s & 1), (s >> 1) & 1);
 
   // ---------------- final flush, left-over (out of range) ids ----------------
-  const unsigned fm = __ballot_sync(0xffffffffu, lane < K && row >= 0 && cnt > 0);
-#pragma unroll
-  for (int k = 0; k < K; ++k)
-    if ((fm >> k) & 1u) {
-      const int row_k = __shfl_sync(0xffffffffu, row, k);
-      flush_row<NV, K>(acc[k], p.P64 + (int64_t)row_k * p.ldP, lane, ldD, atomic);
-    }
+  flush_rows(__ballot_sync(0xffffffffu, lane < K && row >= 0 && cnt > 0));
   // ids >= N are never consumed: poison the row like the gather kernel does (last segment only)
   if (lane < K && row >= 0 && blockIdx.y == gridDim.y - 1 && pos < len) p.P64[(int64_t)row * p.ldP] = NAN;
   if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(p.flags, 1);
@@ -487,7 +505,94 @@ Shape pick_shape(int nv, int64_t n_rows, int sms) {
   return t[n - 1];
 }
 
+// ---- K4-sparse: bucket the permutation ids by slab ----------------------------------------------
+// sample(x = count.cells, size = nnz) (R/haystack_continuous.R:275) yields ids in random order; the slab
+// kernel needs them ascending at slab granularity.  One CTA per permuted row does a counting sort by
+// slab id in shared memory (histogram, scan, scatter) and writes (id, value) pairs in slab order; the
+// pairing id[i] <-> val[i] of the reference is carried along.  Ids outside [0, N) go to an overflow bin
+// at the end of the row, where the slab kernel never consumes them and poisons the row (NaN), as the
+// reference's D[ind, ] would fail.  The order inside a slab follows the atomics, i.e. the fp32 summation
+// order of a row is not fixed run to run (differences ~1e-8 relative on D_KL).
+constexpr int kSortThreads = 512;
+
+__global__ void k_perm_row_ptr(const int64_t* __restrict__ gp, int64_t n_sel, int n_perm, int64_t* __restrict__ rp) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n_rows = n_sel * n_perm;
+  if (row > n_rows) return;
+  if (row == n_rows) {
+    rp[row] = gp[n_sel] * n_perm;
+    return;
+  }
+  const int64_t s = row / n_perm, r = row - s * n_perm;
+  rp[row] = gp[s] * n_perm + r * (gp[s + 1] - gp[s]);
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
+                 const float* __restrict__ vals, const int32_t* __restrict__ ind, int index_base, int64_t N, int S,
+                 int n_bins, int32_t* __restrict__ cols_out, float* __restrict__ vals_out) {
+  extern __shared__ unsigned int hist[];      // [n_bins + 1]; bin n_bins - 1 = overflow
+  __shared__ unsigned int warp_tot[kSortThreads / 32];
+  const int64_t row = blockIdx.x;
+  const int64_t s = row / n_perm;
+  const int64_t beg = rp[row], nnz = rp[row + 1] - beg;
+  const int32_t* in = ind + beg;
+  const float* vin = vals + gp[s];
+  const int tid = threadIdx.x;
+  for (int i = tid; i <= n_bins; i += kSortThreads) hist[i] = 0u;
+  __syncthreads();
+  for (int64_t i = tid; i < nnz; i += kSortThreads) {
+    const int64_t id = (int64_t)in[i] - index_base;
+    const int bin = (id < 0 || id >= N) ? n_bins - 1 : (int)(id / S);
+    atomicAdd(&hist[bin], 1u);
+  }
+  __syncthreads();
+  // exclusive scan of hist[0 .. n_bins): each thread owns a contiguous run
+  const int per = (n_bins + kSortThreads - 1) / kSortThreads;
+  const int lo = hs_min(tid * per, n_bins), hi = hs_min(lo + per, n_bins);
+  unsigned int sum = 0;
+  for (int i = lo; i < hi; ++i) sum += hist[i];
+  unsigned int incl = sum;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned int base = 0;
+  for (int w2 = 0; w2 < warp; ++w2) base += warp_tot[w2];
+  unsigned int run = base + incl - sum;
+  for (int i = lo; i < hi; ++i) {
+    const unsigned int c = hist[i];
+    hist[i] = run;
+    run += c;
+  }
+  __syncthreads();
+  int32_t* co = cols_out + beg;
+  float* vo = vals_out + beg;
+  for (int64_t i = tid; i < nnz; i += kSortThreads) {
+    const int64_t id = (int64_t)in[i] - index_base;
+    const bool bad = id < 0 || id >= N;
+    const int bin = bad ? n_bins - 1 : (int)(id / S);
+    const unsigned int at = atomicAdd(&hist[bin], 1u);
+    co[at] = bad ? 0x7fffffff : (int32_t)id;
+    vo[at] = vin[i];
+  }
+}
+
 }  // namespace
+
+constexpr size_t kSlabFixed = kMaxWarps * 32 * sizeof(uint2) + 64;
+
+// cells per density slab for the resident state
+int hs_slab_cells(const hs_ctx* ctx) {
+  int S = (int)((kMaxSmem - kSlabFixed) / (2 * (size_t)ctx->ldD * sizeof(float)));
+  S = hs_min<int>(S & ~3, 2048);
+  if ((int64_t)S > ctx->N) S = (int)((ctx->N + 3) & ~3LL);
+  return S;
+}
 
 // Sparse rows x resident density matrix -> D_KL.  PERM selects the randomization layout (see k_row_len).
 // out_dev: fp64, n_rows entries (CSR) or n_sel x n_perm column-major (PERM).
@@ -495,7 +600,7 @@ Shape pick_shape(int nv, int64_t n_rows, int sms) {
 // chain the order-independent fallback without a host round trip.
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     const int** flag_dev_out) {
+                     int out_n_perm, int64_t out_n_sel, const int** flag_dev_out) {
   const int64_t n_rows = perm ? n_units * (int64_t)n_perm : n_units;
   if (n_rows <= 0) return HS_OK;
   if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many rows (%lld) for one call", (long long)n_rows);
@@ -506,16 +611,17 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   const int sms = ctx->sm_count;
   const Shape shp = pick_shape(NV, n_rows, sms);
   const int K = shp.k, kWarps = shp.w;
-  const int n_tiles = (int)((n_rows + (int64_t)kWarps * K - 1) / ((int64_t)kWarps * K));
+  // whole waves of CTAs: rows are dealt evenly over waves * sms tiles (slots may stay empty), but a
+  // tile never holds less than one row per warp
+  const int64_t waves = (n_rows + (int64_t)kWarps * K * sms - 1) / ((int64_t)kWarps * K * sms);
+  const int n_tiles = (int)hs_max<int64_t>(1, hs_min<int64_t>(waves * sms, (n_rows + kWarps - 1) / kWarps));
   const int n_bins = n_tiles * kWarps;
   const int64_t n_slots = (int64_t)n_bins * K;
 
   // slab size: two buffers + scratch + barriers within the opt-in shared memory limit
-  const size_t fixed = kMaxWarps * 32 * sizeof(uint2) + 64;
-  int S = (int)((kMaxSmem - fixed) / (2 * (size_t)ldD * sizeof(float)));
-  S = hs_min<int>(S & ~3, 2048);
+  const size_t fixed = kSlabFixed;
+  const int S = hs_slab_cells(ctx);
   if (S < 4) return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d leaves no room for a density slab", G);
-  if ((int64_t)S > ctx->N) S = (int)((ctx->N + 3) & ~3LL);
   const size_t smem = 2 * (size_t)S * ldD * sizeof(float) + fixed;
   // split the cell axis over grid.y when there are too few row tiles to fill the machine
   int n_seg = 1;
@@ -593,8 +699,9 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   const int nacc = (G + 31) / 32;
   const unsigned eb = (unsigned)((n_rows + 7) / 8);
   const double* Q = (const double*)ctx->Q.p;
-  const int np = perm ? n_perm : 0;
-#define HS_EPI(NA) k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_rows, ldP, G, Q, np, n_units, flags, out_dev)
+  const int np = perm ? n_perm : out_n_perm;
+  const int64_t nsel = perm ? n_units : out_n_sel;
+#define HS_EPI(NA) k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_rows, ldP, G, Q, np, nsel, flags, out_dev)
   if (nacc <= 1) HS_EPI(1);
   else if (nacc <= 2) HS_EPI(2);
   else if (nacc <= 3) HS_EPI(3);
@@ -606,4 +713,34 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   HS_LAUNCH_CHECK(ctx);
   if (flag_dev_out) *flag_dev_out = flags;
   return HS_OK;
+}
+
+// Randomization batch, sparse form: bucket every permuted row by slab, then run the slab kernel over
+// the n_sel * n_perm rows.  Returns HS_ERR_STATE-free HS_OK, or a negative "not applicable" marker (-1)
+// when the cell axis has too many slabs for the shared-memory histogram (the caller then gathers).
+int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
+                       const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
+  const int64_t n_rows = n_sel * (int64_t)n_perm;
+  if (n_rows <= 0) return HS_OK;
+  const int S = hs_slab_cells(ctx);
+  if (S < 4) return -1;
+  const int64_t n_slabs = (ctx->N + S - 1) / S;
+  const int n_bins = (int)n_slabs + 1;                     // + overflow bin
+  const size_t smem = sizeof(unsigned int) * (size_t)(n_bins + 1);
+  if (smem > 200 * 1024) return -1;
+  const int64_t n_ids = n_vals_total * n_perm;
+  HS_TRY(hs_ensure(ctx, ctx->perm_rp, sizeof(int64_t) * (size_t)(n_rows + 1)));
+  HS_TRY(hs_ensure(ctx, ctx->perm_cols, sizeof(int32_t) * (size_t)hs_max<int64_t>(n_ids, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->perm_vals, sizeof(float) * (size_t)hs_max<int64_t>(n_ids, 1)));
+  cudaStream_t st = ctx->stream;
+  int64_t* rp = (int64_t*)ctx->perm_rp.p;
+  k_perm_row_ptr<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(gene_ptr_dev, n_sel, n_perm, rp);
+  HS_LAUNCH_CHECK(ctx);
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_perm_slab_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_perm_slab_sort<<<(unsigned)n_rows, kSortThreads, smem, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base,
+                                                                 ctx->N, S, n_bins, (int32_t*)ctx->perm_cols.p,
+                                                                 (float*)ctx->perm_vals.p);
+  HS_LAUNCH_CHECK(ctx);
+  return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, (const int32_t*)ctx->perm_cols.p, (const float*)ctx->perm_vals.p, 0,
+                          out_dev, n_perm, n_sel, nullptr);
 }
