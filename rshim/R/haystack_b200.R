@@ -1,0 +1,63 @@
+# Drop-in replacement of the three hot spans of haystack_continuous_highD()
+# (singleCellHaystack R/haystack_continuous.R:168-186, :199-213, :245-284) by device calls.
+# WRITTEN BLIND (no R in the build environment); see INTEGRATION.md.
+#
+# Usage inside the patched haystack_continuous_highD(), everything else of the function unchanged:
+#
+#   dev <- b200_context()
+#   st  <- b200_density(dev, x, grid.coord, weights.advanced.Q)      # replaces :168-186
+#   bandwidth <- st$bandwidth; Q <- st$Q; density.contributions <- st$densities
+#   D_KL.observed <- if (is.matrix(expression)) b200_dkl_dense(dev, expression)
+#                    else b200_dkl_csr(dev, expression)              # replaces :199-213
+#   all.D_KL.randomized <- b200_randomize(dev, expression, genes.to.randomize,
+#                                         randomization.count, count.cells)   # replaces :245-284
+#
+# The random draws stay in R, in the reference's order (gene-major, permutation-minor), so
+# set.seed() reproducibility is untouched.
+
+b200_context <- function(device = 0L) .Call("hsb_create", as.integer(device), PACKAGE = "haystackB200")
+
+b200_density <- function(dev, x, grid.coord, weights.advanced.Q = NULL, densities = TRUE) {
+  storage.mode(x) <- "double"; storage.mode(grid.coord) <- "double"
+  res <- .Call("hsb_density", dev, x, grid.coord,
+               if (is.null(weights.advanced.Q)) NULL else as.double(weights.advanced.Q),
+               densities, PACKAGE = "haystackB200")
+  names(res) <- c("bandwidth", "Q", "densities")
+  res
+}
+
+b200_dkl_dense <- function(dev, expression) {
+  storage.mode(expression) <- "double"
+  .Call("hsb_dkl_dense", dev, expression, PACKAGE = "haystackB200")
+}
+
+b200_dkl_csr <- function(dev, expression) {          # expression: dgRMatrix
+  .Call("hsb_dkl_csr", dev, expression@p, expression@j, expression@x, PACKAGE = "haystackB200")
+}
+
+b200_randomize <- function(dev, expression, genes.to.randomize, randomization.count, count.cells) {
+  n.sel <- length(genes.to.randomize)
+  if (is.matrix(expression)) {
+    out <- matrix(NA_real_, n.sel, randomization.count)
+    for (i in seq_len(n.sel)) {
+      v <- expression[genes.to.randomize[i], ]
+      # sample(x = v) == v[sample.int(length(v))]: same RNG consumption as the reference (:259)
+      perm <- vapply(seq_len(randomization.count), function(r) sample.int(count.cells), integer(count.cells))
+      out[i, ] <- .Call("hsb_dkl_perm_dense", dev, as.double(v), perm, PACKAGE = "haystackB200")
+    }
+    return(out)
+  }
+  vals <- vector("list", n.sel); inds <- vector("list", n.sel)
+  for (i in seq_len(n.sel)) {
+    g <- genes.to.randomize[i]
+    lo <- expression@p[g] + 1L; hi <- expression@p[g + 1L]
+    nnz <- hi - lo + 1L
+    vals[[i]] <- if (nnz > 0) expression@x[lo:hi] else numeric(0)
+    # column r = sample(x = count.cells, size = nnz), as R/haystack_continuous.R:275
+    inds[[i]] <- as.integer(vapply(seq_len(randomization.count),
+                                   function(r) sample(x = count.cells, size = nnz), integer(nnz)))
+  }
+  gene.ptr <- c(0, cumsum(vapply(vals, length, 0)))
+  .Call("hsb_dkl_perm_csr", dev, as.double(gene.ptr), unlist(vals), unlist(inds),
+        as.integer(randomization.count), PACKAGE = "haystackB200")
+}

@@ -1,0 +1,123 @@
+/* .Call shim between R and libhaystack_b200.so (C ABI: include/haystack_b200.h).
+ *
+ * WRITTEN BLIND: neither the build container nor the GPU boxes have R (no Rinternals.h), so this
+ * file has never been compiled.  It is the binding a maintainer adds to singleCellHaystack to put
+ * the B200 path behind the unchanged haystack() API.  Rules it follows:
+ *   - REAL()/INTEGER() pointers go straight through: R matrices are column-major doubles, dgRMatrix
+ *     slots are @p int, @j int (0-based), @x double -- exactly what the C ABI takes.
+ *   - outputs are allocated with allocVector under PROTECT;
+ *   - the context lives in an external pointer with a finalizer;
+ *   - a non-zero return code becomes Rf_error() AFTER the call returned (never from inside the library).
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+#include <stdint.h>
+
+#include "haystack_b200.h"
+
+static void ctx_finalizer(SEXP ptr) {
+  hs_ctx* ctx = (hs_ctx*)R_ExternalPtrAddr(ptr);
+  if (ctx) hs_destroy(ctx);
+  R_ClearExternalPtr(ptr);
+}
+
+static hs_ctx* get_ctx(SEXP ptr) {
+  hs_ctx* ctx = (hs_ctx*)R_ExternalPtrAddr(ptr);
+  if (!ctx) Rf_error("haystack_b200: context has been destroyed");
+  return ctx;
+}
+
+static void check(hs_ctx* ctx, int rc, const char* what) {
+  if (rc != HS_OK) Rf_error("%s failed (%d): %s", what, rc, hs_last_error(ctx));
+}
+
+SEXP hsb_create(SEXP device) {
+  hs_ctx* ctx = NULL;
+  int rc = hs_create(asInteger(device), &ctx);
+  if (rc != HS_OK) Rf_error("hs_create failed (%d): %s", rc, hs_last_error(NULL));
+  SEXP ptr = PROTECT(R_MakeExternalPtr(ctx, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(ptr, ctx_finalizer, TRUE);
+  UNPROTECT(1);
+  return ptr;
+}
+
+/* x: scaled N x d matrix, grid: G x d matrix, w: NULL or numeric(N), want_dens: logical.
+ * returns list(bandwidth, Q, densities | NULL)  -- R/haystack_continuous.R:168-186 */
+SEXP hsb_density(SEXP sctx, SEXP x, SEXP grid, SEXP w, SEXP want_dens) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t n = nrows(x);
+  const int d = ncols(x), g = nrows(grid);
+  SEXP q = PROTECT(allocVector(REALSXP, g));
+  SEXP dens = R_NilValue;
+  if (asLogical(want_dens)) dens = allocMatrix(REALSXP, (int)n, g);
+  PROTECT(dens);
+  double bw = 0.0;
+  int rc = hs_density(ctx, REAL(x), n, d, REAL(grid), g, isNull(w) ? NULL : REAL(w), &bw, REAL(q),
+                      isNull(dens) ? NULL : REAL(dens), NULL);
+  check(ctx, rc, "hs_density");
+  SEXP out = PROTECT(allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, ScalarReal(bw));
+  SET_VECTOR_ELT(out, 1, q);
+  SET_VECTOR_ELT(out, 2, dens);
+  UNPROTECT(3);
+  return out;
+}
+
+/* expression: numeric matrix genes x cells -- loop R/haystack_continuous.R:202-206 */
+SEXP hsb_dkl_dense(SEXP sctx, SEXP expression) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t m = nrows(expression);
+  SEXP out = PROTECT(allocVector(REALSXP, m));
+  check(ctx, hs_dkl_dense(ctx, REAL(expression), m, m, REAL(out)), "hs_dkl_dense");
+  UNPROTECT(1);
+  return out;
+}
+
+/* dgRMatrix slots -- loop R/haystack_continuous.R:207-212 */
+SEXP hsb_dkl_csr(SEXP sctx, SEXP p, SEXP j, SEXP xval) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t m = XLENGTH(p) - 1;
+  SEXP out = PROTECT(allocVector(REALSXP, m));
+  check(ctx, hs_dkl_csr(ctx, INTEGER(p), 0, INTEGER(j), REAL(xval), m, REAL(out)), "hs_dkl_csr");
+  UNPROTECT(1);
+  return out;
+}
+
+/* v: numeric(N); perm: integer N x R matrix, column r = sample.int(N) -- R/haystack_continuous.R:250-265 */
+SEXP hsb_dkl_perm_dense(SEXP sctx, SEXP v, SEXP perm) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int r = ncols(perm);
+  SEXP out = PROTECT(allocVector(REALSXP, r));
+  check(ctx, hs_dkl_perm_dense(ctx, REAL(v), INTEGER(perm), r, 1, REAL(out)), "hs_dkl_perm_dense");
+  UNPROTECT(1);
+  return out;
+}
+
+/* gene_ptr: numeric(S+1) prefix offsets (doubles: may exceed int), val: numeric, ind: integer vector
+ * laid out gene by gene as nnz_s x R column-major blocks -- R/haystack_continuous.R:266-283 */
+SEXP hsb_dkl_perm_csr(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP ind, SEXP n_perm) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t s = XLENGTH(gene_ptr) - 1;
+  const int r = asInteger(n_perm);
+  int64_t* gp = (int64_t*)R_alloc((size_t)s + 1, sizeof(int64_t));
+  for (int64_t i = 0; i <= s; ++i) gp[i] = (int64_t)REAL(gene_ptr)[i];
+  SEXP out = PROTECT(allocMatrix(REALSXP, (int)s, r));
+  check(ctx, hs_dkl_perm_csr(ctx, gp, s, REAL(val), INTEGER(ind), r, 1, REAL(out)), "hs_dkl_perm_csr");
+  UNPROTECT(1);
+  return out;
+}
+
+static const R_CallMethodDef call_methods[] = {
+    {"hsb_create", (DL_FUNC)&hsb_create, 1},
+    {"hsb_density", (DL_FUNC)&hsb_density, 5},
+    {"hsb_dkl_dense", (DL_FUNC)&hsb_dkl_dense, 2},
+    {"hsb_dkl_csr", (DL_FUNC)&hsb_dkl_csr, 4},
+    {"hsb_dkl_perm_dense", (DL_FUNC)&hsb_dkl_perm_dense, 3},
+    {"hsb_dkl_perm_csr", (DL_FUNC)&hsb_dkl_perm_csr, 5},
+    {NULL, NULL, 0}};
+
+void R_init_haystackB200(DllInfo* dll) {
+  R_registerRoutines(dll, NULL, call_methods, NULL, NULL);
+  R_useDynamicSymbols(dll, FALSE);
+}

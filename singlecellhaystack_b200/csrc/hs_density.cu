@@ -173,17 +173,28 @@ k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, const double
 }
 
 // Q = (colsum + pseudo) / sum   (R/haystack_continuous.R:184-186); fixed summation order.
+// Step 1: one block per grid column sums the per-block partials (strided, then a fixed tree).
 __global__ void __launch_bounds__(256)
-k_q_finalize(const double* __restrict__ qpart, int nblocks, int G, double* __restrict__ Q) {
+k_q_colsum(const double* __restrict__ qpart, int nblocks, int G, double* __restrict__ Q) {
+  __shared__ double red[256];
+  const int j = blockIdx.x;
+  double local = 0.0;
+  for (int b = threadIdx.x; b < nblocks; b += 256) local += qpart[(int64_t)b * G + j];
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) Q[j] = red[0] + HS_PSEUDO;
+}
+
+// Step 2: normalise.
+__global__ void __launch_bounds__(256)
+k_q_finalize(int G, double* __restrict__ Q) {
   __shared__ double red[256];
   double local = 0.0;
-  for (int j = threadIdx.x; j < G; j += 256) {
-    double q = 0.0;
-    for (int b = 0; b < nblocks; ++b) q += qpart[(int64_t)b * G + j];
-    q += HS_PSEUDO;
-    Q[j] = q;
-    local += q;
-  }
+  for (int j = threadIdx.x; j < G; j += 256) local += Q[j];
   red[threadIdx.x] = local;
   __syncthreads();
   for (int s = 128; s > 0; s >>= 1) {
@@ -255,7 +266,9 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
                                                      want_dens64 ? (double*)ctx->dens64.p : nullptr,
                                                      (double*)ctx->qpart.p);
   HS_LAUNCH_CHECK(ctx);
-  k_q_finalize<<<1, 256, 0, st>>>((const double*)ctx->qpart.p, nblocks, G, (double*)ctx->Q.p);
+  k_q_colsum<<<G, 256, 0, st>>>((const double*)ctx->qpart.p, nblocks, G, (double*)ctx->Q.p);
+  HS_LAUNCH_CHECK(ctx);
+  k_q_finalize<<<1, 256, 0, st>>>(G, (double*)ctx->Q.p);
   HS_LAUNCH_CHECK(ctx);
 
   // the bandwidth rides behind Q so that one collective moves both (hs_density_buffers)

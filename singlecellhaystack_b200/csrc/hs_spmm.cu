@@ -527,10 +527,15 @@ __global__ void k_perm_row_ptr(const int64_t* __restrict__ gp, int64_t n_sel, in
   rp[row] = gp[s] * n_perm + r * (gp[s + 1] - gp[s]);
 }
 
-__global__ void __launch_bounds__(kSortThreads)
+// exact id / S for 0 <= id < 2^31 and S <= 2048: magic = ceil(2^40 / S)
+__device__ __forceinline__ int div_magic(uint32_t id, uint64_t magic) { return (int)(((uint64_t)id * magic) >> 40); }
+
+constexpr int kSortUnroll = 8;   // independent loads in flight per thread
+
+__global__ void __launch_bounds__(kSortThreads, 2)
 k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
-                 const float* __restrict__ vals, const int32_t* __restrict__ ind, int index_base, int64_t N, int S,
-                 int n_bins, int32_t* __restrict__ cols_out, float* __restrict__ vals_out) {
+                 const float* __restrict__ vals, const int32_t* __restrict__ ind, int index_base, int64_t N,
+                 uint64_t magic, int n_bins, int32_t* __restrict__ cols_out, float* __restrict__ vals_out) {
   extern __shared__ unsigned int hist[];      // [n_bins + 1]; bin n_bins - 1 = overflow
   __shared__ unsigned int warp_tot[kSortThreads / 32];
   const int64_t row = blockIdx.x;
@@ -541,10 +546,21 @@ k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp,
   const int tid = threadIdx.x;
   for (int i = tid; i <= n_bins; i += kSortThreads) hist[i] = 0u;
   __syncthreads();
-  for (int64_t i = tid; i < nnz; i += kSortThreads) {
-    const int64_t id = (int64_t)in[i] - index_base;
-    const int bin = (id < 0 || id >= N) ? n_bins - 1 : (int)(id / S);
-    atomicAdd(&hist[bin], 1u);
+  auto bin_of = [&](int32_t raw) {
+    const int64_t id = (int64_t)raw - index_base;
+    return (id < 0 || id >= N) ? n_bins - 1 : div_magic((uint32_t)id, magic);
+  };
+  constexpr int64_t kStep = (int64_t)kSortThreads * kSortUnroll;
+  for (int64_t i0 = 0; i0 < nnz; i0 += kStep) {
+    int32_t raw[kSortUnroll];
+#pragma unroll
+    for (int u = 0; u < kSortUnroll; ++u) {
+      const int64_t i = i0 + (int64_t)u * kSortThreads + tid;
+      raw[u] = i < nnz ? __ldg(in + i) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kSortUnroll; ++u)
+      if (i0 + (int64_t)u * kSortThreads + tid < nnz) atomicAdd(&hist[bin_of(raw[u])], 1u);
   }
   __syncthreads();
   // exclusive scan of hist[0 .. n_bins): each thread owns a contiguous run
@@ -572,13 +588,26 @@ k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp,
   __syncthreads();
   int32_t* co = cols_out + beg;
   float* vo = vals_out + beg;
-  for (int64_t i = tid; i < nnz; i += kSortThreads) {
-    const int64_t id = (int64_t)in[i] - index_base;
-    const bool bad = id < 0 || id >= N;
-    const int bin = bad ? n_bins - 1 : (int)(id / S);
-    const unsigned int at = atomicAdd(&hist[bin], 1u);
-    co[at] = bad ? 0x7fffffff : (int32_t)id;
-    vo[at] = vin[i];
+  for (int64_t i0 = 0; i0 < nnz; i0 += kStep) {
+    int32_t raw[kSortUnroll];
+    float v[kSortUnroll];
+#pragma unroll
+    for (int u = 0; u < kSortUnroll; ++u) {
+      const int64_t i = i0 + (int64_t)u * kSortThreads + tid;
+      raw[u] = i < nnz ? __ldg(in + i) : 0;
+      v[u] = i < nnz ? __ldg(vin + i) : 0.f;
+    }
+    unsigned int at[kSortUnroll];
+#pragma unroll
+    for (int u = 0; u < kSortUnroll; ++u)
+      at[u] = (i0 + (int64_t)u * kSortThreads + tid < nnz) ? atomicAdd(&hist[bin_of(raw[u])], 1u) : 0u;
+#pragma unroll
+    for (int u = 0; u < kSortUnroll; ++u)
+      if (i0 + (int64_t)u * kSortThreads + tid < nnz) {
+        const int64_t id = (int64_t)raw[u] - index_base;
+        co[at[u]] = (id < 0 || id >= N) ? 0x7fffffff : (int32_t)id;
+        vo[at[u]] = v[u];
+      }
   }
 }
 
@@ -737,8 +766,9 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
   k_perm_row_ptr<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(gene_ptr_dev, n_sel, n_perm, rp);
   HS_LAUNCH_CHECK(ctx);
   HS_CUDA(ctx, cudaFuncSetAttribute(k_perm_slab_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint64_t magic = ((1ull << 40) + (uint64_t)S - 1) / (uint64_t)S;
   k_perm_slab_sort<<<(unsigned)n_rows, kSortThreads, smem, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base,
-                                                                 ctx->N, S, n_bins, (int32_t*)ctx->perm_cols.p,
+                                                                 ctx->N, magic, n_bins, (int32_t*)ctx->perm_cols.p,
                                                                  (float*)ctx->perm_vals.p);
   HS_LAUNCH_CHECK(ctx);
   return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, (const int32_t*)ctx->perm_cols.p, (const float*)ctx->perm_vals.p, 0,
