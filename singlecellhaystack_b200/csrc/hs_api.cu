@@ -158,7 +158,7 @@ void hs_destroy(hs_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->D32, &ctx->Q, &ctx->sq, &ctx->rowmin, &ctx->nearest, &ctx->sel, &ctx->qpart,
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
-                    &ctx->ptrs, &ctx->dense_in, &ctx->spmm_ws, &ctx->cols32, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals};
+                    &ctx->ptrs, &ctx->spmm_ws, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -312,6 +312,7 @@ int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
   ctx->G = n_grid;
   ctx->ldD = ldD;
   ctx->bw = bw;
+  ctx->tiles_valid = false;
   return HS_OK;
 }
 
@@ -456,13 +457,29 @@ int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, d
     return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_dense: bad arguments");
   if (n_genes == 0) return HS_OK;
   const int64_t N = ctx->N;
-  HS_TRY(hs_ensure(ctx, ctx->dense_in, sizeof(double) * (size_t)n_genes * N));
+  // upload in column blocks through the fp64 staging buffers, converting to fp32 on the device
+  const int64_t cols_per_chunk = hs_max<int64_t>(1, ((int64_t)16 << 20) / n_genes);
+  const size_t stage_elems = (size_t)hs_min<int64_t>(cols_per_chunk, N) * n_genes;
+  for (int b = 0; b < 2; ++b) HS_TRY(hs_ensure(ctx, ctx->stage_x[b], sizeof(double) * stage_elems));
+  HS_TRY(hs_ensure(ctx, ctx->dense32, sizeof(float) * (size_t)n_genes * N));
   HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)n_genes));
-  cudaStream_t st = ctx->stream;
-  HS_CUDA(ctx, cudaMemcpy2DAsync(ctx->dense_in.p, sizeof(double) * n_genes, expr, sizeof(double) * ld,
-                                 sizeof(double) * n_genes, (size_t)N, cudaMemcpyHostToDevice, st));
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
+  HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));
+  int k = 0;
+  for (int64_t c0 = 0; c0 < N; c0 += cols_per_chunk, ++k) {
+    const int b = k & 1;
+    const int64_t nc = hs_min<int64_t>(cols_per_chunk, N - c0);
+    if (k >= 2) HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[b], 0));
+    HS_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_x[b].p, sizeof(double) * n_genes, expr + c0 * ld, sizeof(double) * ld,
+                                   sizeof(double) * n_genes, (size_t)nc, cudaMemcpyHostToDevice, cs));
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], cs));
+    HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[b], 0));
+    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, (float*)ctx->dense32.p + c0 * n_genes, nc * n_genes));
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+  }
   ScopedTimer tm(ctx, HS_T_DENSE);
-  HS_TRY(hs_run_dense_f64(ctx, (const double*)ctx->dense_in.p, n_genes, n_genes, (double*)ctx->out.p));
+  HS_TRY(hs_run_dense_f32(ctx, (const float*)ctx->dense32.p, n_genes, n_genes, (double*)ctx->out.p));
   tm.stop();
   HS_CUDA(ctx, cudaMemcpyAsync(dkl_out, ctx->out.p, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
   HS_CUDA(ctx, cudaStreamSynchronize(st));

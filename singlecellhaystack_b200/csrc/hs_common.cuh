@@ -54,14 +54,18 @@ struct hs_ctx {
   DevBuf qpart;     // [blocks][G] fp64
   DevBuf dens64;    // [G][N] fp64 (only when density_out requested)
   DevBuf xin, gin, win;        // uploaded x / grid / w_q
-  DevBuf part;      // [ksplit][rows][ldP] fp64 partial P
+  DevBuf part;      // [rows][ldP] fp64 column sums P
+  DevBuf simt_part; // [ksplit][rows][ldP] fp64 split-K partials of the SIMT dense kernel
   DevBuf out;       // fp64 results
   DevBuf stage_j[2], stage_x[2];  // H2D staging (int32 ids, fp64 values)
   DevBuf vals32;    // fp32 values
   DevBuf ptrs;      // int64 row pointers
-  DevBuf dense_in;  // uploaded dense expression (fp64 col-major)
   DevBuf spmm_ws;   // slab kernel: flags, sort keys, slot table, cub workspace
   DevBuf cols32;    // uploaded column / cell ids (host-pointer entry points)
+  DevBuf dtile_hi, dtile_lo;   // fp16 hi / lo density operands pre-tiled for the tensor-core kernels
+  bool tiles_valid = false;    // the tiles match the resident density matrix
+  DevBuf umma_flags;
+  DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, slab-bucketed ids / values
   void* pinned = nullptr;      // small pinned host bounce buffer
   size_t pinned_cap = 0;
@@ -109,8 +113,11 @@ int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const fl
                int64_t n_rows, double* out_dev);
 int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                     const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
+// tensor-core dense contraction (hs_umma.cu); -1 = shape not supported
+int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, const float* v_dev,
+                      const int32_t* perm_dev, int index_base, int64_t n_rows, double* out_dev,
+                      const int** flag_dev_out);
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
-int hs_run_dense_f64(hs_ctx* ctx, const double* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
                       int index_base, double* out_dev);
 int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n);

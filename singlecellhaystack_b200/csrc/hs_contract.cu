@@ -7,6 +7,7 @@
 // structured genes is ~ 1/2 sum (P-Q)^2/Q and amplifies column-sum error ~30x).  The epilogue
 // is fp64 and never writes P to HBM.
 #include <math.h>
+#include <stdlib.h>
 
 #include "hs_common.cuh"
 
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(256)
 k_dense_partial(const TE* __restrict__ E, int64_t ld, const float* __restrict__ v,
                 const int32_t* __restrict__ perm, int index_base, int64_t n_rows, int64_t N,
                 const float* __restrict__ D, int ldD, int G, int cells_per_split, int ldP,
-                double* __restrict__ part) {
+                const int* __restrict__ run_if_flag, double* __restrict__ part) {
+  if (run_if_flag && !(*run_if_flag & 1)) return;   // chained behind the tensor-core kernel
   __shared__ __align__(16) float As[kTK][kTM + 4];
   __shared__ __align__(16) float Bs[kTK][kTN];
   const int tid = threadIdx.x;
@@ -200,7 +202,8 @@ k_dense_partial(const TE* __restrict__ E, int64_t ld, const float* __restrict__ 
 template <int NACC>
 __global__ void __launch_bounds__(256)
 k_rows_epilogue(const double* __restrict__ part, int n_split, int64_t n_rows, int ldP, int G,
-                const double* __restrict__ Q, double* __restrict__ out) {
+                const double* __restrict__ Q, const int* __restrict__ run_if_flag, double* __restrict__ out) {
+  if (run_if_flag && !(*run_if_flag & 1)) return;
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -259,13 +262,14 @@ int launch_rows_gather(hs_ctx* ctx, const int64_t* ptr, const int32_t* cols, con
   return HS_OK;
 }
 
-int launch_rows_epilogue(hs_ctx* ctx, const double* part, int n_split, int64_t n_rows, int ldP, double* out) {
+int launch_rows_epilogue(hs_ctx* ctx, const double* part, int n_split, int64_t n_rows, int ldP, const int* run_if_flag,
+                         double* out) {
   const int G = ctx->G;
   const int nacc = (G + 31) / 32;
   const int blocks = (int)((n_rows + 7) / 8);
   const double* Q = (const double*)ctx->Q.p;
 #define HS_EPI_CASE(NA)                                                                               \
-  k_rows_epilogue<NA><<<blocks, 256, 0, ctx->stream>>>(part, n_split, n_rows, ldP, G, Q, out)
+  k_rows_epilogue<NA><<<blocks, 256, 0, ctx->stream>>>(part, n_split, n_rows, ldP, G, Q, run_if_flag, out)
   if (nacc <= 1) HS_EPI_CASE(1);
   else if (nacc <= 2) HS_EPI_CASE(2);
   else if (nacc <= 3) HS_EPI_CASE(3);
@@ -281,7 +285,7 @@ int launch_rows_epilogue(hs_ctx* ctx, const double* part, int n_split, int64_t n
 
 template <typename TE, bool PERM>
 int launch_dense(hs_ctx* ctx, const TE* E, int64_t ld, const float* v, const int32_t* perm, int index_base,
-                 int64_t n_rows, double* out) {
+                 int64_t n_rows, const int* run_if_flag, double* out) {
   if (n_rows <= 0) return HS_OK;
   const int G = ctx->G;
   const int64_t N = ctx->N;
@@ -294,13 +298,14 @@ int launch_dense(hs_ctx* ctx, const TE* E, int64_t ld, const float* v, const int
   int n_split = (int)hs_max<int64_t>(1, hs_min<int64_t>(hs_min<int64_t>(want, max_split), 65535));
   int64_t cells_per_split = ((N + n_split - 1) / n_split + 255) / 256 * 256;
   n_split = (int)((N + cells_per_split - 1) / cells_per_split);
-  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_split * n_rows * ldP));
+  HS_TRY(hs_ensure(ctx, ctx->simt_part, sizeof(double) * (size_t)n_split * n_rows * ldP));
   dim3 grid(row_tiles, n_split, col_tiles);
   k_dense_partial<TE, PERM><<<grid, 256, 0, ctx->stream>>>(E, ld, v, perm, index_base, n_rows, N,
                                                             (const float*)ctx->D32.p, ctx->ldD, G,
-                                                            (int)cells_per_split, ldP, (double*)ctx->part.p);
+                                                            (int)cells_per_split, ldP, run_if_flag,
+                                                            (double*)ctx->simt_part.p);
   HS_LAUNCH_CHECK(ctx);
-  return launch_rows_epilogue(ctx, (const double*)ctx->part.p, n_split, n_rows, ldP, out);
+  return launch_rows_epilogue(ctx, (const double*)ctx->simt_part.p, n_split, n_rows, ldP, run_if_flag, out);
 }
 
 }  // namespace
@@ -325,15 +330,28 @@ int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int
                                   index_base, nullptr, out_dev);
 }
 
-int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {
-  return launch_dense<float, false>(ctx, e_dev, ld, nullptr, nullptr, 0, n_genes, out_dev);
+// Dense forms: tensor-core kernel first; the fp32 SIMT kernel is chained behind it and only does work
+// when the tensor-core kernel flagged an fp16 overflow (or cannot take the shape / is disabled).
+static bool umma_disabled() {
+  const char* e = getenv("HS_DISABLE_UMMA");
+  return e && *e && *e != '0';
 }
 
-int hs_run_dense_f64(hs_ctx* ctx, const double* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {
-  return launch_dense<double, false>(ctx, e_dev, ld, nullptr, nullptr, 0, n_genes, out_dev);
+int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {
+  const int* flag = nullptr;
+  if (!umma_disabled()) {
+    const int rc = hs_run_dense_umma(ctx, false, e_dev, ld, nullptr, nullptr, 0, n_genes, out_dev, &flag);
+    if (rc != HS_OK && rc != -1) return rc;
+  }
+  return launch_dense<float, false>(ctx, e_dev, ld, nullptr, nullptr, 0, n_genes, flag, out_dev);
 }
 
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm, int index_base,
                       double* out_dev) {
-  return launch_dense<float, true>(ctx, (const float*)nullptr, 0, v_dev, perm_dev, index_base, n_perm, out_dev);
+  const int* flag = nullptr;
+  if (!umma_disabled()) {
+    const int rc = hs_run_dense_umma(ctx, true, nullptr, 0, v_dev, perm_dev, index_base, n_perm, out_dev, &flag);
+    if (rc != HS_OK && rc != -1) return rc;
+  }
+  return launch_dense<float, true>(ctx, (const float*)nullptr, 0, v_dev, perm_dev, index_base, n_perm, flag, out_dev);
 }

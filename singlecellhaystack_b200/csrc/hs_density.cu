@@ -277,5 +277,6 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
   ctx->N = N;
   ctx->G = G;
   ctx->ldD = ldD;
+  ctx->tiles_valid = false;
   return HS_OK;
 }

@@ -1,0 +1,478 @@
+// K2 / K4-dense: gene x grid contraction on the 5th-generation tensor cores (tcgen05 + TMEM).
+//   P[row, j] = sum_c A[row, c] * D[c, j]
+//     dense:  A[row, c] = E[row + c * ld]                 R/haystack_continuous.R:357 (colSums(D * w))
+//     perm :  A[row, c] = v[perm[c + row * N] - base]     R/haystack_continuous.R:259 (sample(x = v))
+//
+// Precision: a single 16-bit operand pass violates the 1e-5 D_KL tolerance, so both
+// operands are split into two fp16 terms, x = hi + lo * 2^-11 (22 significant bits), and three MMAs per
+// K step accumulate   acc0 += A_hi * D_hi,   acc1 += A_hi * D_lo + A_lo * D_hi   in fp32 TMEM.  The tensor
+// core truncates (rounds toward zero) every accumulating MMA, a bias that grows with the number of MMAs
+// summed into one TMEM value and does not cancel between grid columns (measured: 32 MMAs per sum give
+// 4e-5 relative D_KL error, 4 MMAs give 5e-6 = the fp32 SIMT kernel's level).  TMEM is therefore drained
+// after every stage (64 cells) into round-to-nearest fp32 register sums, and those every 1024 cells into
+// fp64 (global atomics): the same three levels as the CSR kernel.  The operand scales (s_E = 2^-3 for A, 2^14 for D) keep realistic expression values and all
+// densities >= 4e-9 in fp16's normal range; an A value that still overflows fp16 raises a device flag
+// and the caller reruns the fp32 SIMT kernel instead (no silent loss).
+//
+// Layout: both operands are MN-major (E is gene-contiguous, D is grid-column-contiguous), 128B swizzle.
+//   element (mn, k) of a 128 x 64 tile at byte  ((k/8)*2 + mn/64) * 1024 + (k%8) * 128
+//                                             + (((mn%64)/8) ^ (k%8)) * 16 + (mn%8) * 2
+//   => descriptor LBO = 1024 B (between the two 64-wide MN atoms), SBO = 2048 B (between groups of 8 k).
+// D_hi / D_lo are pre-tiled in HBM in exactly this layout by k_density_tiles (one 16 KB block per 64
+// cells), so a stage's B operand is one cp.async.bulk per term (1-D TMA, no tensor map).
+// Warp roles (16 warps): 0-3 build the A tiles (load, split, swizzled st.shared, fence.proxy.async),
+// 4 streams the B tiles, 5 owns TMEM and issues the MMAs, 8-15 drain TMEM and accumulate.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "hs_common.cuh"
+
+namespace {
+
+constexpr int kTileM = 128;          // rows (genes / permutations) per CTA
+constexpr int kTileN = 128;          // grid columns per CTA (G <= 128)
+constexpr int kBK = 64;              // cells per pipeline stage
+constexpr int kStages = 3;
+constexpr int kTileBytes = kTileM * kBK * 2;          // 16 KB per fp16 operand term
+constexpr int kStageBytes = 4 * kTileBytes;           // A_hi, A_lo, B_hi, B_lo
+constexpr int kDrainBlocks = 1;      // TMEM -> registers after every stage (64 cells = 4 accumulating MMAs per sum)
+constexpr int kFlushDrains = 16;     // registers -> fp64 every 16 drains (1024 cells)
+constexpr int kUmmaThreads = 512;
+constexpr float kScaleA = 0.125f;            // 2^-3
+constexpr float kScaleD = 16384.f;           // 2^14
+constexpr float kLoScale = 2048.f;           // 2^11
+constexpr uint32_t kLbo = 1024, kSbo = 2048;
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate, M = 128, N = 128, K = 16
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: MN-major, 128B swizzle, LBO / SBO as above, sm_100 version bit
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(kLbo >> 4) << 16) | ((uint64_t)(kSbo >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32, A = B = F16, both MN-major, N = 128, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | (1u << 15) | (1u << 16) | ((kTileN >> 3) << 17) |
+                            ((kTileM >> 4) << 24);
+
+// byte offset of the 16-byte chunk holding elements (8*mg .. 8*mg+7, k) of a 128 x 64 MN-major SW128 tile
+__device__ __host__ __forceinline__ uint32_t chunk_off(int mg, int k) {
+  const int mi = mg >> 3, c8 = mg & 7, kg = k >> 3, k8 = k & 7;
+  return (uint32_t)(((kg * 2 + mi) << 10) + (k8 << 7) + ((c8 ^ k8) << 4));
+}
+
+// split 8 scaled floats into fp16 hi / lo (lo pre-multiplied by 2^11) and pack each as one 16-byte chunk
+__device__ __forceinline__ bool split8(const float (&x)[8], uint4& hi, uint4& lo) {
+  __half2 h[4], l[4];
+  bool over = false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = x[2 * i], b = x[2 * i + 1];
+    h[i] = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h[i]);
+    over |= (isinf(hf.x) && !isinf(a)) || (isinf(hf.y) && !isinf(b));
+    l[i] = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+  }
+  hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
+                  *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
+  lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
+                  *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
+  return over;
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// ---- pre-tiled fp16 density operands ---------------------------------------------------------------
+// D32 [N][ldD] fp32  ->  Dh, Dl: one 16 KB tile per 64 cells, rows = grid columns (zero beyond G / N)
+__global__ void __launch_bounds__(256)
+k_density_tiles(const float* __restrict__ D32, int64_t N, int ldD, int G, unsigned char* __restrict__ Dh,
+                unsigned char* __restrict__ Dl) {
+  const int64_t kb = blockIdx.x;
+  // 16 column groups x 64 cells = 1024 chunks per tile
+  for (int task = threadIdx.x; task < 1024; task += 256) {
+    const int mg = task & 15, k = task >> 4;
+    const int64_t cell = kb * kBK + k;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int j = 8 * mg + i;
+      x[i] = (cell < N && j < G) ? D32[cell * ldD + j] * kScaleD : 0.f;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const size_t off = (size_t)kb * kTileBytes + chunk_off(mg, k);
+    *reinterpret_cast<uint4*>(Dh + off) = hi;
+    *reinterpret_cast<uint4*>(Dl + off) = lo;
+  }
+}
+
+// ---- main kernel -----------------------------------------------------------------------------------
+struct UmmaParams {
+  // A operand source
+  const float* E;          // dense: [rows + cells * ld]
+  int64_t ld;
+  const float* v;          // perm: values [N]
+  const int32_t* perm;     // perm: [N x n_rows] column-major
+  int index_base;
+  int64_t n_rows;
+  int64_t N;               // cells
+  // B operand
+  const unsigned char* Dh;
+  const unsigned char* Dl;
+  // split-K
+  int64_t kblocks_per_seg;
+  // output
+  double* P64;             // [n_rows][ldP], zeroed by the caller
+  int ldP;
+  int G;
+  int* flags;              // bit 0: fp16 overflow of an A value -> caller reruns the SIMT kernel
+};
+
+template <bool PERM>
+__global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // 1024-byte aligned operand stages (swizzle atoms), then barriers
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_a = [&](int s) { return bar_base + 8u * s; };
+  auto full_b = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto empty = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tmem_full = [&](int b) { return bar_base + 8u * (3 * kStages + b); };
+  auto tmem_empty = [&](int b) { return bar_base + 8u * (3 * kStages + 2 + b); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  const int64_t total_kb = (p.N + kBK - 1) / kBK;
+  const int64_t kb_begin = (int64_t)blockIdx.y * p.kblocks_per_seg;
+  const int64_t kb_end = hs_min<int64_t>(total_kb, kb_begin + p.kblocks_per_seg);
+  const int n_kb = (int)hs_max<int64_t>(0, kb_end - kb_begin);
+  const int n_drains = (n_kb + kDrainBlocks - 1) / kDrainBlocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_a(s), 4);
+      mbar_init(full_b(s), 1);
+      mbar_init(empty(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full(b), 1);
+      mbar_init(tmem_empty(b), 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ================= A producers =================
+    bool over = false;
+    for (int i = 0; i < n_kb; ++i) {
+      const int s = i % kStages;
+      if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
+      const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kTileBytes;
+      const int64_t c0 = (kb_begin + i) * kBK;
+      if (!PERM) {
+        // task = (row group of 8, cell): lanes 0-15 cover 128 rows of one cell, 16-31 the next cell
+        const bool vec = ((p.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.E) & 15) == 0);
+#pragma unroll 2
+        for (int t = threadIdx.x; t < 1024; t += 128) {
+          const int mg = t & 15, k = t >> 4;
+          const int64_t cell = c0 + k, r = row0 + 8 * mg;
+          float x[8];
+          if (cell < p.N && r + 8 <= p.n_rows && vec) {
+            const float4 u = __ldg(reinterpret_cast<const float4*>(p.E + r + cell * p.ld));
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.E + r + 4 + cell * p.ld));
+            x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w.x; x[5] = w.y; x[6] = w.z; x[7] = w.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = (cell < p.N && r + e < p.n_rows) ? __ldg(p.E + r + e + cell * p.ld) : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[e] *= kScaleA;
+          uint4 hi, lo;
+          over |= split8(x, hi, lo);
+          const uint32_t off = chunk_off(mg, k);
+          sts_u4(a_hi + off, hi);
+          sts_u4(a_lo + off, lo);
+        }
+      } else {
+        // task = (row group of 8, cell): lanes run over 32 consecutive cells (coalesced index loads)
+        for (int t = threadIdx.x; t < 1024; t += 128) {
+          const int k = (t & 31) + 32 * ((t >> 5) & 1), mg = t >> 6;
+          const int64_t cell = c0 + k, r = row0 + 8 * mg;
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a = 0.f;
+            if (cell < p.N && r + e < p.n_rows) {
+              const int64_t src = (int64_t)__ldg(p.perm + cell + (r + e) * p.N) - p.index_base;
+              a = (src >= 0 && src < p.N) ? __ldg(p.v + src) : __int_as_float(0x7fc00000);
+            }
+            x[e] = a * kScaleA;
+          }
+          uint4 hi, lo;
+          over |= split8(x, hi, lo);
+          const uint32_t off = chunk_off(mg, k);
+          sts_u4(a_hi + off, hi);
+          sts_u4(a_lo + off, lo);
+        }
+      }
+      fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_a(s));
+    }
+    if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(p.flags, 1);
+  } else if (warp == 4) {
+    // ================= B loader =================
+    if (lane == 0) {
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % kStages;
+        if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
+        const uint32_t b_hi = smem_base + s * kStageBytes + 2 * kTileBytes;
+        const size_t off = (size_t)(kb_begin + i) * kTileBytes;
+        mbar_arrive_expect_tx(full_b(s), 2 * kTileBytes);
+        bulk_g2s(b_hi, p.Dh + off, kTileBytes, full_b(s));
+        bulk_g2s(b_hi + kTileBytes, p.Dl + off, kTileBytes, full_b(s));
+      }
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      for (int i = 0; i < n_kb; ++i) {
+        const int s = i % kStages;
+        const int d = i / kDrainBlocks, buf = d & 1;
+        const bool first = (i % kDrainBlocks) == 0;
+        if (first && d >= 2) {
+          mbar_wait(tmem_empty(buf), ((d >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(full_a(s), (i / kStages) & 1);
+        mbar_wait(full_b(s), (i / kStages) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_base + s * kStageBytes;
+        const uint32_t acc0 = tmem_base + (uint32_t)(buf * 256), acc1 = acc0 + 128;
+#pragma unroll
+        for (int k16 = 0; k16 < kBK / 16; ++k16) {
+          const uint32_t koff = (uint32_t)k16 * 2u * kSbo;
+          const uint64_t a_hi = make_desc(st + koff), a_lo = make_desc(st + kTileBytes + koff);
+          const uint64_t b_hi = make_desc(st + 2 * kTileBytes + koff), b_lo = make_desc(st + 3 * kTileBytes + koff);
+          const uint32_t accum = (first && k16 == 0) ? 0u : 1u;
+          umma_f16(acc0, a_hi, b_hi, kIdesc, accum);
+          umma_f16(acc1, a_hi, b_lo, kIdesc, accum);
+          umma_f16(acc1, a_lo, b_hi, kIdesc, 1u);
+        }
+        umma_commit(empty(s));                                   // stage free once these MMAs retire
+        if ((i % kDrainBlocks) == kDrainBlocks - 1 || i == n_kb - 1) umma_commit(tmem_full(buf));
+      }
+    }
+  } else if (warp >= 8) {
+    // ================= epilogue: TMEM -> fp32 registers -> fp64 =================
+    const int q = warp & 3, half = (warp - 8) >> 2;            // TMEM lane quarter, column half
+    const int64_t row = row0 + 32 * q + lane;
+    const int col0 = 64 * half;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+    float acc2[64];
+#pragma unroll
+    for (int c = 0; c < 64; ++c) acc2[c] = 0.f;
+    const double unscale = 1.0 / ((double)kScaleA * (double)kScaleD);
+    auto flush = [&]() {
+      if (row < p.n_rows) {
+        double* prow = p.P64 + row * p.ldP;
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          if (col0 + c < p.G) atomicAdd(prow + col0 + c, (double)acc2[c] * unscale);
+      }
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc2[c] = 0.f;
+    };
+    for (int d = 0; d < n_drains; ++d) {
+      const int buf = d & 1;
+      mbar_wait(tmem_full(buf), (d >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float a[32];
+        tmem_ld32(lane_addr + (uint32_t)(buf * 256 + 128 + col0 + 32 * h), a);       // cross terms, scale 2^-11
+#pragma unroll
+        for (int c = 0; c < 32; ++c) a[c] *= (1.0f / kLoScale);
+        float m[32];
+        tmem_ld32(lane_addr + (uint32_t)(buf * 256 + col0 + 32 * h), m);             // hi * hi
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc2[32 * h + c] += m[c] + a[c];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(buf));
+      if ((d % kFlushDrains) == kFlushDrains - 1) flush();
+    }
+    flush();
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+constexpr size_t kUmmaSmem = 1024 + (size_t)kStages * kStageBytes + 16 * 8 + 64;
+
+template <int NACC>
+__global__ void __launch_bounds__(256)
+k_p64_kl(const double* __restrict__ P64, int64_t n_rows, int ldP, int G, const double* __restrict__ Q,
+         const int* __restrict__ flags, double* __restrict__ out) {
+  if (*flags & 1) return;   // the SIMT rerun produces the output
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  double pr[NACC];
+#pragma unroll
+  for (int a = 0; a < NACC; ++a) {
+    const int j = lane + 32 * a;
+    pr[a] = j < G ? P64[row * ldP + j] : 0.0;
+  }
+  const double kl = hs_kl_epilogue<NACC>(pr, Q, G, lane);
+  if (lane == 0) out[row] = kl;
+}
+
+}  // namespace
+
+// (Re)build the pre-tiled fp16 density operands for the resident state.
+static int ensure_density_tiles(hs_ctx* ctx) {
+  if (ctx->tiles_valid) return HS_OK;
+  const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
+  HS_TRY(hs_ensure(ctx, ctx->dtile_hi, (size_t)total_kb * kTileBytes));
+  HS_TRY(hs_ensure(ctx, ctx->dtile_lo, (size_t)total_kb * kTileBytes));
+  k_density_tiles<<<(unsigned)total_kb, 256, 0, ctx->stream>>>((const float*)ctx->D32.p, ctx->N, ctx->ldD, ctx->G,
+                                                               (unsigned char*)ctx->dtile_hi.p,
+                                                               (unsigned char*)ctx->dtile_lo.p);
+  HS_LAUNCH_CHECK(ctx);
+  ctx->tiles_valid = true;
+  return HS_OK;
+}
+
+// Tensor-core dense contraction + KL.  Returns -1 when the shape is not supported (G > 128): the caller
+// then uses the SIMT kernel.  On success *flag_dev_out points at the device flag whose bit 0 asks for a
+// SIMT rerun (fp16 overflow of an expression value).
+int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, const float* v_dev,
+                      const int32_t* perm_dev, int index_base, int64_t n_rows, double* out_dev,
+                      const int** flag_dev_out) {
+  if (n_rows <= 0) return HS_OK;
+  if (ctx->G > kTileN) return -1;
+  HS_TRY(ensure_density_tiles(ctx));
+  const int ldP = kTileN;
+  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_rows * ldP));
+  HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_rows * ldP, st));
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
+  const int row_tiles = (int)((n_rows + kTileM - 1) / kTileM);
+  const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
+  // split the cell axis until the grid covers the machine; segments are whole drain windows
+  int64_t n_seg = hs_max<int64_t>(1, ctx->sm_count / row_tiles);
+  int64_t kb_per_seg = (total_kb + n_seg - 1) / n_seg;
+  kb_per_seg = (kb_per_seg + kDrainBlocks - 1) / kDrainBlocks * kDrainBlocks;
+  n_seg = (total_kb + kb_per_seg - 1) / kb_per_seg;
+  UmmaParams prm;
+  prm.E = e_dev;
+  prm.ld = ld;
+  prm.v = v_dev;
+  prm.perm = perm_dev;
+  prm.index_base = index_base;
+  prm.n_rows = n_rows;
+  prm.N = ctx->N;
+  prm.Dh = (const unsigned char*)ctx->dtile_hi.p;
+  prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
+  prm.kblocks_per_seg = kb_per_seg;
+  prm.P64 = (double*)ctx->part.p;
+  prm.ldP = ldP;
+  prm.G = ctx->G;
+  prm.flags = (int*)ctx->umma_flags.p;
+  dim3 grid(row_tiles, (unsigned)n_seg);
+  if (perm) {
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
+    k_dense_umma<true><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
+  } else {
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
+    k_dense_umma<false><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
+  }
+  HS_LAUNCH_CHECK(ctx);
+  const unsigned eb = (unsigned)((n_rows + 7) / 8);
+  k_p64_kl<4><<<eb, 256, 0, st>>>((const double*)ctx->part.p, n_rows, ldP, ctx->G, (const double*)ctx->Q.p,
+                                  (const int*)ctx->umma_flags.p, out_dev);
+  HS_LAUNCH_CHECK(ctx);
+  if (flag_dev_out) *flag_dev_out = (const int*)ctx->umma_flags.p;
+  return HS_OK;
+}
