@@ -60,7 +60,8 @@ struct hs_ctx {
   DevBuf stage_j[2], stage_x[2];  // H2D staging (int32 ids, fp64 values)
   DevBuf vals32;    // fp32 values
   DevBuf ptrs;      // int64 row pointers
-  DevBuf spmm_ws;   // slab kernel: flags, sort keys, slot table, cub workspace
+  DevBuf spmm_ws;   // sparse contraction: flags, sort keys, cub workspace
+  DevBuf spmm_slots;   // slab kernel: slot table
   DevBuf cols32;    // uploaded column / cell ids (host-pointer entry points)
   DevBuf dtile_hi, dtile_lo;   // fp16 hi / lo density operands pre-tiled for the tensor-core kernels
   bool tiles_valid = false;    // the tiles match the resident density matrix
@@ -106,7 +107,7 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
 // slab-staged sparse contraction (hs_spmm.cu); see there for the arguments
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     int out_n_perm, int64_t out_n_sel, const int** flag_dev_out);
+                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out);
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,
@@ -117,6 +118,9 @@ int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int
 int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, const float* v_dev,
                       const int32_t* perm_dev, int index_base, int64_t n_rows, double* out_dev,
                       const int** flag_dev_out);
+bool hs_umma_disabled();   // HS_DISABLE_UMMA=1 forces the SIMT kernels (A/B comparisons)
+int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
+                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP, int* flags);
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
                       int index_base, double* out_dev);

@@ -316,7 +316,7 @@ int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const fl
   // slab-staged kernel; rows it flags (ids not ascending / negative) are redone by the gather kernel,
   // chained on the device-side flag so no host round trip is needed
   const int* flag = nullptr;
-  HS_TRY(hs_run_slab_spmm(ctx, false, p_dev, n_rows, 1, j_dev, x_dev, 0, out_dev, 0, 0, &flag));
+  HS_TRY(hs_run_slab_spmm(ctx, false, p_dev, n_rows, 1, j_dev, x_dev, 0, out_dev, 0, 0, /*allow_umma=*/true, &flag));
   return launch_rows_gather<false>(ctx, p_dev, j_dev, x_dev, n_rows, 1, n_rows, 0, flag, out_dev);
 }
 
@@ -332,14 +332,14 @@ int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int
 
 // Dense forms: tensor-core kernel first; the fp32 SIMT kernel is chained behind it and only does work
 // when the tensor-core kernel flagged an fp16 overflow (or cannot take the shape / is disabled).
-static bool umma_disabled() {
+bool hs_umma_disabled() {
   const char* e = getenv("HS_DISABLE_UMMA");
   return e && *e && *e != '0';
 }
 
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev) {
   const int* flag = nullptr;
-  if (!umma_disabled()) {
+  if (!hs_umma_disabled()) {
     const int rc = hs_run_dense_umma(ctx, false, e_dev, ld, nullptr, nullptr, 0, n_genes, out_dev, &flag);
     if (rc != HS_OK && rc != -1) return rc;
   }
@@ -349,7 +349,7 @@ int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t l
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm, int index_base,
                       double* out_dev) {
   const int* flag = nullptr;
-  if (!umma_disabled()) {
+  if (!hs_umma_disabled()) {
     const int rc = hs_run_dense_umma(ctx, true, nullptr, 0, v_dev, perm_dev, index_base, n_perm, out_dev, &flag);
     if (rc != HS_OK && rc != -1) return rc;
   }

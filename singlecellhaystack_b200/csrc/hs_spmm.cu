@@ -19,6 +19,7 @@
 // then runs the order-independent gather kernel (hs_contract.cu) instead.
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <stdlib.h>
 
 #include "hs_common.cuh"
 
@@ -113,6 +114,7 @@ __global__ void k_row_len(const int64_t* __restrict__ ptr, int64_t n_rows, int n
 template <bool PERM>
 __global__ void k_build_slots(const int64_t* __restrict__ ptr, const int32_t* __restrict__ sorted_rows,
                               int64_t n_rows, int n_perm, int n_bins, int K, Slots sl) {
+  // sorted_rows / n_rows: the (sub)range of the length-sorted row list this launch covers
   const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= (int64_t)n_bins * K) return;
   const int bin = (int)(slot / K), k = (int)(slot - (int64_t)bin * K);
@@ -136,6 +138,16 @@ __global__ void k_build_slots(const int64_t* __restrict__ ptr, const int32_t* __
   sl.voff[slot] = vo;
   sl.len[slot] = len;
   sl.row[slot] = row;
+}
+
+// rows (sorted by descending length) with at least `thr` stored entries -> out[0]
+__global__ void k_count_ge(const uint32_t* __restrict__ keys_desc, int64_t n, uint32_t thr, int* __restrict__ out) {
+  int64_t lo = 0, hi = n;   // first index with key < thr
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (keys_desc[mid] >= thr) lo = mid + 1; else hi = mid;
+  }
+  out[0] = (int)lo;
 }
 
 // ---- main kernel -----------------------------------------------------------------------------------
@@ -629,7 +641,7 @@ int hs_slab_cells(const hs_ctx* ctx) {
 // chain the order-independent fallback without a host round trip.
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     int out_n_perm, int64_t out_n_sel, const int** flag_dev_out) {
+                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out) {
   const int64_t n_rows = perm ? n_units * (int64_t)n_perm : n_units;
   if (n_rows <= 0) return HS_OK;
   if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many rows (%lld) for one call", (long long)n_rows);
@@ -638,37 +650,18 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   const int NV = nvq <= 1 ? 1 : nvq <= 2 ? 2 : nvq <= 4 ? 4 : 8;
   if (nvq > 8) return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d exceeds the supported maximum of 1024", G);
   const int sms = ctx->sm_count;
-  const Shape shp = pick_shape(NV, n_rows, sms);
-  const int K = shp.k, kWarps = shp.w;
-  // whole waves of CTAs: rows are dealt evenly over waves * sms tiles (slots may stay empty), but a
-  // tile never holds less than one row per warp
-  const int64_t waves = (n_rows + (int64_t)kWarps * K * sms - 1) / ((int64_t)kWarps * K * sms);
-  const int n_tiles = (int)hs_max<int64_t>(1, hs_min<int64_t>(waves * sms, (n_rows + kWarps - 1) / kWarps));
-  const int n_bins = n_tiles * kWarps;
-  const int64_t n_slots = (int64_t)n_bins * K;
-
-  // slab size: two buffers + scratch + barriers within the opt-in shared memory limit
   const size_t fixed = kSlabFixed;
   const int S = hs_slab_cells(ctx);
   if (S < 4) return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d leaves no room for a density slab", G);
   const size_t smem = 2 * (size_t)S * ldD * sizeof(float) + fixed;
-  // split the cell axis over grid.y when there are too few row tiles to fill the machine
-  int n_seg = 1;
-  const int64_t total_slabs = (ctx->N + S - 1) / S;
-  if (n_tiles * 2 <= sms) n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms / n_tiles, total_slabs / 4));
-  const int64_t seg_cells = ((total_slabs + n_seg - 1) / n_seg) * S;
-  n_seg = (int)((ctx->N + seg_cells - 1) / seg_cells);
 
-  // ---- scratch ----
+  // ---- row lengths, sorted descending ----
   const int ldP = ldD;
   size_t cub_bytes = 0;
   cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                             (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows, 0, 32, ctx->stream);
   const size_t keys_b = ((size_t)n_rows * 4 + 255) & ~(size_t)255;
-  const size_t slots_b = ((size_t)n_slots * 8 + 255) & ~(size_t)255;
-  const size_t slots4_b = ((size_t)n_slots * 4 + 255) & ~(size_t)255;
-  const size_t need = 256 + 4 * keys_b + 2 * slots_b + 2 * slots4_b + ((cub_bytes + 255) & ~(size_t)255);
-  HS_TRY(hs_ensure(ctx, ctx->spmm_ws, need));
+  HS_TRY(hs_ensure(ctx, ctx->spmm_ws, 256 + 4 * keys_b + ((cub_bytes + 255) & ~(size_t)255)));
   HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_rows * ldP));
   char* w = (char*)ctx->spmm_ws.p;
   int* flags = (int*)w;                    w += 256;
@@ -676,16 +669,10 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   uint32_t* keys_out = (uint32_t*)w;       w += keys_b;
   int32_t* rows_in = (int32_t*)w;          w += keys_b;
   int32_t* rows_out = (int32_t*)w;         w += keys_b;
-  Slots sl;
-  sl.coff = (int64_t*)w;                   w += slots_b;
-  sl.voff = (int64_t*)w;                   w += slots_b;
-  sl.len = (int32_t*)w;                    w += slots4_b;
-  sl.row = (int32_t*)w;                    w += slots4_b;
   void* cub_ws = w;
   cudaStream_t st = ctx->stream;
   HS_CUDA(ctx, cudaMemsetAsync(flags, 0, 256, st));
   HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_rows * ldP, st));
-
   const int tb = 256;
   if (perm)
     k_row_len<true><<<(unsigned)((n_rows + tb - 1) / tb), tb, 0, st>>>(ptr_dev, n_rows, n_perm, keys_in, rows_in, flags);
@@ -695,10 +682,61 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   HS_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(cub_ws, cub_bytes, keys_in, keys_out, rows_in, rows_out,
                                                          (int)n_rows, 0, 32, st));
   ctx->launches += 3;   // cub: histogram + onesweep passes (counted once as a family)
+
+  // ---- the densest rows go to the tensor cores (hs_umma.cu): above a few % non-zeros the dense-equivalent
+  //      MMA work is cheaper than gathering a density row per non-zero.  Whole 128-row tiles only. ----
+  int64_t n_dense = 0;
+  if (allow_umma && !perm && G <= 128 && !hs_umma_disabled()) {
+    // Off unless asked for: with the scalar scatter producer the tensor path does not beat the slab kernel
+    // yet (profiles/README.md); HS_UMMA_MIN_DENSITY=<fraction> enables it.
+    const char* e = getenv("HS_UMMA_MIN_DENSITY");
+    const double min_density = (e && *e) ? atof(e) : 2.0;
+    const uint32_t thr = (uint32_t)hs_max<int64_t>(32, (int64_t)ceil(min_density * (double)ctx->N));
+    int n_ge = 0;
+    if (min_density <= 1.0) {
+      k_count_ge<<<1, 1, 0, st>>>(keys_out, n_rows, thr, flags + 1);
+      HS_LAUNCH_CHECK(ctx);
+      HS_CUDA(ctx, cudaMemcpyAsync(&n_ge, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+      HS_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    n_dense = ((int64_t)n_ge / 128) * 128;
+    if (n_dense > 0) {
+      const int rc = hs_run_csr_umma(ctx, rows_out, n_dense, ptr_dev, cols_dev, vals_dev, col_base,
+                                     (double*)ctx->part.p, ldP, flags);
+      if (rc == -1) n_dense = 0;
+      else if (rc != HS_OK) return rc;
+    }
+  }
+
+  // ---- the remaining rows: slab kernel ----
+  const int64_t n_sub = n_rows - n_dense;
+  const Shape shp = pick_shape(NV, hs_max<int64_t>(n_sub, 1), sms);
+  const int K = shp.k, kWarps = shp.w;
+  // whole waves of CTAs: rows are dealt evenly over waves * sms tiles (slots may stay empty), but a
+  // tile never holds less than one row per warp
+  const int64_t waves = hs_max<int64_t>(1, (n_sub + (int64_t)kWarps * K * sms - 1) / ((int64_t)kWarps * K * sms));
+  const int n_tiles = (int)hs_max<int64_t>(1, hs_min<int64_t>(waves * sms, (n_sub + kWarps - 1) / kWarps));
+  const int n_bins = n_tiles * kWarps;
+  const int64_t n_slots = (int64_t)n_bins * K;
+  // split the cell axis over grid.y when there are too few row tiles to fill the machine
+  int n_seg = 1;
+  const int64_t total_slabs = (ctx->N + S - 1) / S;
+  if (n_tiles * 2 <= sms) n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms / n_tiles, total_slabs / 4));
+  const int64_t seg_cells = ((total_slabs + n_seg - 1) / n_seg) * S;
+  n_seg = (int)((ctx->N + seg_cells - 1) / seg_cells);
+  const size_t slots_b = ((size_t)n_slots * 8 + 255) & ~(size_t)255;
+  const size_t slots4_b = ((size_t)n_slots * 4 + 255) & ~(size_t)255;
+  HS_TRY(hs_ensure(ctx, ctx->spmm_slots, 2 * slots_b + 2 * slots4_b));
+  Slots sl;
+  w = (char*)ctx->spmm_slots.p;
+  sl.coff = (int64_t*)w;                   w += slots_b;
+  sl.voff = (int64_t*)w;                   w += slots_b;
+  sl.len = (int32_t*)w;                    w += slots4_b;
+  sl.row = (int32_t*)w;                    w += slots4_b;
   if (perm)
-    k_build_slots<true><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out, n_rows, n_perm, n_bins, K, sl);
+    k_build_slots<true><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out + n_dense, n_sub, n_perm, n_bins, K, sl);
   else
-    k_build_slots<false><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out, n_rows, n_perm, n_bins, K, sl);
+    k_build_slots<false><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out + n_dense, n_sub, n_perm, n_bins, K, sl);
   HS_LAUNCH_CHECK(ctx);
 
   SpmmParams prm;
@@ -717,6 +755,7 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   prm.flags = flags;
 
 #define HS_SPMM_CASE(NVv, Kv, Wv) \
+  if (n_sub <= 0) {} else \
   if (NV == NVv && K == Kv && kWarps == Wv) { HS_TRY((launch_spmm<NVv, Kv, Wv>(ctx, prm, n_tiles, smem))); } else
   HS_SPMM_CASE(1, 1, 16) HS_SPMM_CASE(1, 2, 16) HS_SPMM_CASE(1, 4, 16) HS_SPMM_CASE(1, 8, 16) HS_SPMM_CASE(1, 17, 12)
   HS_SPMM_CASE(2, 1, 16) HS_SPMM_CASE(2, 2, 16) HS_SPMM_CASE(2, 4, 16) HS_SPMM_CASE(2, 8, 12)
@@ -772,5 +811,5 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
                                                                  (float*)ctx->perm_vals.p);
   HS_LAUNCH_CHECK(ctx);
   return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, (const int32_t*)ctx->perm_cols.p, (const float*)ctx->perm_vals.p, 0,
-                          out_dev, n_perm, n_sel, nullptr);
+                          out_dev, n_perm, n_sel, /*allow_umma=*/false, nullptr);   // ids are only slab-sorted
 }

@@ -32,7 +32,9 @@ namespace {
 constexpr int kTileM = 128;          // rows (genes / permutations) per CTA
 constexpr int kTileN = 128;          // grid columns per CTA (G <= 128)
 constexpr int kBK = 64;              // cells per pipeline stage
-constexpr int kStages = 3;
+constexpr int kStagesDense = 3;   // dense / perm producers
+constexpr int kStagesCsr = 2;     // csr producer: the third stage's shared memory holds the entry rings
+constexpr int kRing = 64;         // csr: entries per row ring (>= cells per stage, so a stage never outruns it)
 constexpr int kTileBytes = kTileM * kBK * 2;          // 16 KB per fp16 operand term
 constexpr int kStageBytes = 4 * kTileBytes;           // A_hi, A_lo, B_hi, B_lo
 constexpr int kDrainBlocks = 1;      // TMEM -> registers after every stage (64 cells = 4 accumulating MMAs per sum)
@@ -179,7 +181,13 @@ struct UmmaParams {
   const float* v;          // perm: values [N]
   const int32_t* perm;     // perm: [N x n_rows] column-major
   int index_base;
-  int64_t n_rows;
+  // csr: tile row t is matrix row sorted_rows[t] (rows sorted by descending length)
+  const int32_t* sorted_rows;
+  const int64_t* ptr;
+  const int32_t* cols;
+  const float* vals;
+  int col_base;
+  int64_t n_rows;          // rows covered by the tiles (dense / perm: matrix rows; csr: dense-ish rows)
   int64_t N;               // cells
   // B operand
   const unsigned char* Dh;
@@ -190,16 +198,37 @@ struct UmmaParams {
   double* P64;             // [n_rows][ldP], zeroed by the caller
   int ldP;
   int G;
-  int* flags;              // bit 0: fp16 overflow of an A value -> caller reruns the SIMT kernel
+  int* flags;              // bit 0: caller must rerun on the fallback kernel (fp16 overflow of an A value;
+                           //        csr: column ids not ascending)
 };
 
-template <bool PERM>
+enum { kModeDense = 0, kModePerm = 1, kModeCsr = 2 };
+
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t r;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts_u16(uint32_t a, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
+}
+
+template <int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams p) {
+  constexpr bool PERM = MODE == kModePerm;
+  constexpr int kStages = MODE == kModeCsr ? kStagesCsr : kStagesDense;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand stages (swizzle atoms), then barriers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t ring_base = smem_u32(smem + kStages * kStageBytes + 256);   // csr mode: 2 x 32 KB entry rings
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_a = [&](int s) { return bar_base + 8u * s; };
@@ -237,6 +266,138 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   if (warp < 4) {
     // ================= A producers =================
     bool over = false;
+    if (MODE == kModeCsr) {
+      // Scatter producer: thread r owns tile row r.  Rows are dense-ish (>= a few % non-zero), so the
+      // dense-equivalent MMA work beats gathering D rows per non-zero.  Each stage: the 8 threads of a
+      // row group zero its 16-byte chunks (8 cells each, hi and lo), then every thread walks its row's
+      // ascending (col, val) run and drops the split value into (row, cell).  Entries are fetched four
+      // at a time with the next four always in flight.
+      const int r = threadIdx.x, mg = r >> 3, sub = r & 7;
+      const int64_t trow = row0 + r;
+      const int rowid = trow < p.n_rows ? p.sorted_rows[trow] : -1;
+      int64_t pos = 0, end = 0;
+      if (rowid >= 0) {
+        pos = p.ptr[rowid];
+        end = p.ptr[rowid + 1];
+        const int64_t cb = kb_begin * kBK;
+        if (cb > 0) {   // first stored column >= segment start (rows are ascending)
+          int64_t lo = pos, hi = end;
+          while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)p.cols[mid] - p.col_base < cb) lo = mid + 1; else hi = mid;
+          }
+          pos = lo;
+        }
+      }
+      // Per-thread ring of kRing (col, val) entries in shared memory, filled with 4-byte cp.async copies.
+      // All threads top their rings up at the same point (the start of a stage), eight commit groups
+      // each (empty ones included), so the copies issue as converged warp instructions and
+      // "wait_group 8" at the next stage start means "everything requested before this stage has landed".
+      // The lines a row will need ~256 entries ahead are prefetched into L2, so the cp.async copies see L2
+      // rather than HBM latency.
+      const uint32_t ring_c = ring_base + 4u * r;                      // slot stride 512 B (128 threads)
+      const uint32_t ring_v = ring_base + 128u * kRing * 4u + 4u * r;
+      const int64_t pos0 = pos;
+      int64_t head = pos, tail = pos, ready = pos, pf = pos;
+      bool violation = false;
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+      for (int i = 0; i < n_kb; ++i) {
+        // ---- L2 prefetch and ring top-up (converged) ----
+#pragma unroll 1
+        for (int it = 0; it < 4 && pf < end && pf < head + 320; ++it, pf += 32) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cols + pf));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vals + pf));
+        }
+        const int64_t prev_head = head;
+#pragma unroll
+        for (int g8 = 0; g8 < kRing / 8; ++g8) {
+          if (head - tail <= kRing - 8 && head < end) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (head + j < end) {
+                const uint32_t slot = (uint32_t)((head + j - pos0) & (kRing - 1)) * 512u;
+                cp_async4(ring_c + slot, p.cols + head + j);
+                cp_async4(ring_v + slot, p.vals + head + j);
+              }
+            head += 8;
+          }
+          cp_async_commit();
+        }
+        cp_async_wait<kRing / 8>();
+        ready = hs_min<int64_t>(prev_head, end);
+        const int s = i % kStages;
+        if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
+        const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kTileBytes;
+        const int64_t c0 = (kb_begin + i) * kBK;
+        const int c_hi = (int)hs_min<int64_t>(c0 + kBK, p.N);   // ids >= N are never consumed (-> NaN below)
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          const uint32_t off = chunk_off(mg, 8 * sub + kk);
+          sts_u4(a_hi + off, zero4);
+          sts_u4(a_lo + off, zero4);
+        }
+        __syncwarp();   // a row group's 8 threads are consecutive lanes
+        bool more = tail < end;
+        while (more) {
+          if (tail >= ready) {          // a row denser than the ring's lead: wait for what was just requested
+            if (tail >= head && head < end) {   // ring ran dry inside a stage (> 56 entries in 64 cells)
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (head + j < end) {
+                  const uint32_t slot = (uint32_t)((head + j - pos0) & (kRing - 1)) * 512u;
+                  cp_async4(ring_c + slot, p.cols + head + j);
+                  cp_async4(ring_v + slot, p.vals + head + j);
+                }
+              cp_async_commit();
+              head += 8;
+            }
+            cp_async_wait<0>();
+            ready = hs_min<int64_t>(head, end);
+          }
+          // up to four entries per trip: the ring reads are independent, the scatter is in order
+          int c[4];
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t slot = (uint32_t)((tail + j - pos0) & (kRing - 1)) * 512u;
+            c[j] = (tail + j < ready) ? (int)lds_u32(ring_c + slot) - p.col_base : 0x7fffffff;
+            v[j] = __uint_as_float(lds_u32(ring_v + slot));
+          }
+          int used = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (used == j && c[j] < c_hi) {
+              if (c[j] >= (int)c0) {
+                const float x = v[j] * kScaleA;
+                const __half h = __float2half_rn(x);
+                const float hf = __half2float(h);
+                over |= isinf(hf) && !isinf(x);
+                const __half l = __float2half_rn((x - hf) * kLoScale);
+                const uint32_t off = chunk_off(mg, c[j] - (int)c0) + 2u * sub;
+                sts_u16(a_hi + off, __half_as_ushort(h));
+                sts_u16(a_lo + off, __half_as_ushort(l));
+              } else {
+                violation = true;   // an id before this block: the row is not ascending (or negative)
+              }
+              used = j + 1;
+            }
+          }
+          tail += used;
+          // stop at the first entry of a later block; go on if the trip ended on the ring's ready edge
+          more = tail < end && (used == 4 || tail >= ready);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a(s));
+      }
+      cp_async_wait<0>();
+      // entries left after the last block of the last segment carry ids >= N: poison the row
+      if (rowid >= 0 && blockIdx.y == gridDim.y - 1 && tail < end) {
+        const int c = (int)lds_u32(ring_c + (uint32_t)((tail - pos0) & (kRing - 1)) * 512u) - p.col_base;
+        if (tail < head && c != 0x7fffffff) atomicAdd(p.P64 + (int64_t)rowid * p.ldP, (double)NAN);
+      }
+      if (__any_sync(0xffffffffu, violation || over) && lane == 0) atomicOr(p.flags, 1);
+    } else
     for (int i = 0; i < n_kb; ++i) {
       const int s = i % kStages;
       if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
@@ -339,7 +500,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   } else if (warp >= 8) {
     // ================= epilogue: TMEM -> fp32 registers -> fp64 =================
     const int q = warp & 3, half = (warp - 8) >> 2;            // TMEM lane quarter, column half
-    const int64_t row = row0 + 32 * q + lane;
+    const int64_t trow = row0 + 32 * q + lane;
+    const int64_t row = (MODE == kModeCsr) ? (trow < p.n_rows ? (int64_t)p.sorted_rows[trow] : (int64_t)-1) : trow;
     const int col0 = 64 * half;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     float acc2[64];
@@ -347,7 +509,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
     for (int c = 0; c < 64; ++c) acc2[c] = 0.f;
     const double unscale = 1.0 / ((double)kScaleA * (double)kScaleD);
     auto flush = [&]() {
-      if (row < p.n_rows) {
+      if (row >= 0 && trow < p.n_rows) {
         double* prow = p.P64 + row * p.ldP;
 #pragma unroll
         for (int c = 0; c < 64; ++c)
@@ -387,7 +549,8 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   }
 }
 
-constexpr size_t kUmmaSmem = 1024 + (size_t)kStages * kStageBytes + 16 * 8 + 64;
+constexpr size_t kUmmaSmem = 1024 + (size_t)kStagesDense * kStageBytes + 256;
+constexpr size_t kUmmaSmemCsr = 1024 + (size_t)kStagesCsr * kStageBytes + 256 + 2 * 128 * kRing * 4;
 
 template <int NACC>
 __global__ void __launch_bounds__(256)
@@ -445,7 +608,7 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   int64_t kb_per_seg = (total_kb + n_seg - 1) / n_seg;
   kb_per_seg = (kb_per_seg + kDrainBlocks - 1) / kDrainBlocks * kDrainBlocks;
   n_seg = (total_kb + kb_per_seg - 1) / kb_per_seg;
-  UmmaParams prm;
+  UmmaParams prm = {};
   prm.E = e_dev;
   prm.ld = ld;
   prm.v = v_dev;
@@ -462,11 +625,11 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   prm.flags = (int*)ctx->umma_flags.p;
   dim3 grid(row_tiles, (unsigned)n_seg);
   if (perm) {
-    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
-    k_dense_umma<true><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModePerm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
+    k_dense_umma<kModePerm><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
   } else {
-    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
-    k_dense_umma<false><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
+    k_dense_umma<kModeDense><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
   }
   HS_LAUNCH_CHECK(ctx);
   const unsigned eb = (unsigned)((n_rows + 7) / 8);
@@ -474,5 +637,42 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
                                   (const int*)ctx->umma_flags.p, out_dev);
   HS_LAUNCH_CHECK(ctx);
   if (flag_dev_out) *flag_dev_out = (const int*)ctx->umma_flags.p;
+  return HS_OK;
+}
+
+// Tensor-core contraction of the n_dense densest CSR rows (tile row t = matrix row sorted_rows_dev[t]).
+// Adds into P64 (fp64 column sums, [rows][ldP], zeroed by the caller); flags bit 0 requests the fallback.
+// Returns -1 when the shape is not supported (G > 128).
+int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
+                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP, int* flags) {
+  if (n_dense <= 0) return HS_OK;
+  if (ctx->G > kTileN) return -1;
+  HS_TRY(ensure_density_tiles(ctx));
+  const int row_tiles = (int)((n_dense + kTileM - 1) / kTileM);
+  const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
+  // about two waves of CTAs; a segment is at least 64 blocks long
+  int64_t n_seg = hs_max<int64_t>(1, (2 * (int64_t)ctx->sm_count + row_tiles - 1) / row_tiles);
+  n_seg = hs_min<int64_t>(n_seg, hs_max<int64_t>(1, total_kb / 64));
+  const int64_t kb_per_seg = (total_kb + n_seg - 1) / n_seg;
+  n_seg = (total_kb + kb_per_seg - 1) / kb_per_seg;
+  UmmaParams prm = {};
+  prm.sorted_rows = sorted_rows_dev;
+  prm.ptr = ptr_dev;
+  prm.cols = cols_dev;
+  prm.vals = vals_dev;
+  prm.col_base = col_base;
+  prm.n_rows = n_dense;
+  prm.N = ctx->N;
+  prm.Dh = (const unsigned char*)ctx->dtile_hi.p;
+  prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
+  prm.kblocks_per_seg = kb_per_seg;
+  prm.P64 = P64;
+  prm.ldP = ldP;
+  prm.G = ctx->G;
+  prm.flags = flags;
+  dim3 grid(row_tiles, (unsigned)n_seg);
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModeCsr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemCsr));
+  k_dense_umma<kModeCsr><<<grid, kUmmaThreads, kUmmaSmemCsr, ctx->stream>>>(prm);
+  HS_LAUNCH_CHECK(ctx);
   return HS_OK;
 }
