@@ -421,8 +421,7 @@ def run_b200(a):
     value = m_total / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (K3 CSR contraction), algorithmic bytes per launch ----
-    ldd = (g + 3) // 4 * 4
-    k3_bytes = 8.0 * nnz + 8.0 * (m_local + 1) + 8.0 * m_local + 4.0 * n * ldd
+    k3_bytes = 8.0 * nnz + 8.0 * (m_local + 1) + 8.0 * m_local + 4.0 * n * g      # algorithmic: G floats per cell
     peaks_file = ROOT / "MEASURED_PEAKS.json"
     if peaks_file.exists():
         peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
@@ -431,7 +430,7 @@ def run_b200(a):
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = k3_bytes / (k3_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": _ncu_traffic(), "kernel": "k_rows_gather_kl<4,false> (hs_dkl_csr_dev)", "kernel_ms": k3_ms,
+                "traffic": _ncu_traffic(), "kernel": "k_slab_spmm (hs_dkl_csr_dev: slab-staged CSR contraction + KL epilogue)", "kernel_ms": k3_ms,
                 "algorithmic_bytes": k3_bytes, "peak_source": peak_src}
 
     # ---- end to end through the host-pointer C ABI (pinned host inputs, H2D inside the timed region) ----

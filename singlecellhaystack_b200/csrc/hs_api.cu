@@ -279,7 +279,7 @@ int hs_density_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, void** d_dev, i
   if (n_cells <= 0 || n_grid <= 0 || n_grid > 1024 || n_cells > 2147483647LL || !d_dev || !q_dev)
     return hs_fail(ctx, HS_ERR_INVALID, "hs_density_buffers: bad arguments");
   HS_TRY(set_device(ctx));
-  const int ldD = (n_grid + 3) & ~3;
+  const int ldD = hs_ld_for_grid(n_grid);
   if (!(ctx->N == n_cells && ctx->G == n_grid && ctx->ldD == ldD && ctx->D32.p && ctx->Q.p)) {
     ctx->N = 0;
     HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)n_grid + 64));
@@ -297,7 +297,7 @@ int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
   HS_TRY(set_device(ctx));
   if (n_cells <= 0 || n_grid <= 0 || !ctx->D32.p || !ctx->Q.p)
     return hs_fail(ctx, HS_ERR_STATE, "hs_density_commit: call hs_density_buffers first");
-  const int ldD = (n_grid + 3) & ~3;
+  const int ldD = hs_ld_for_grid(n_grid);
   if (ctx->D32.cap < sizeof(float) * (size_t)n_cells * ldD || ctx->Q.cap < sizeof(double) * (size_t)(n_grid + 1))
     return hs_fail(ctx, HS_ERR_STATE, "hs_density_commit: buffers were reserved for a smaller shape");
   double bw = 0.0;

@@ -222,7 +222,7 @@ int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n) {
 
 int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
                    const double* wq_dev, bool want_dens64) {
-  const int ldD = (G + 3) & ~3;
+  const int ldD = hs_ld_for_grid(G);
   const int nblocks = (int)((N + kCellsPerBlock - 1) / kCellsPerBlock);
   HS_TRY(hs_ensure(ctx, ctx->sq, sizeof(double) * (size_t)N * G));
   HS_TRY(hs_ensure(ctx, ctx->rowmin, sizeof(double) * (size_t)N));
