@@ -1,0 +1,181 @@
+"""Multi-GPU host layer: one process per GPU (torch.distributed), genes sharded across ranks.
+
+The path shards naturally: every gene's D_KL depends only on its own row plus the
+shared density state, so there is exactly one exchange step on each side of the scoring --
+  rank 0 runs the density stage, the density matrix / Q / bandwidth are broadcast (NCCL over NVLink
+  between the contexts' own device buffers: DeviceContext.density_broadcast),
+  every rank scores a contiguous, nnz-balanced gene slice and the permuted rows of the selected
+  genes it owns, and D_KL / the randomized matrix are all-gathered.
+No collective sits inside a kernel.  Everything here is SPMD: all ranks call with the same host inputs
+(each rank only uploads its own slice) and all ranks return the same result object.
+
+The compute calls go through a small backend protocol (density / density_broadcast / dkl_csr /
+dkl_dense / dkl_perm_csr / dkl_perm_dense) implemented by `DeviceContext`; the CPU tests plug in a
+checker-backed stand-in to exercise the sharding and gathering logic over gloo.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+
+import numpy as np
+
+from . import haystack as _hs
+from . import sparse as _sparse
+from . import splinefit as _fit
+
+__all__ = ["plan_gene_shards", "owner_of", "haystack_continuous_highD_sharded"]
+
+
+def plan_gene_shards(work: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous gene ranges with (nearly) equal work.  `work[g]` is the cost of gene g (stored
+    entries for a dgRMatrix; 1 per gene for a dense matrix).  Returns `world + 1` boundaries;
+    rank r owns genes [b[r], b[r+1])."""
+    work = np.asarray(work, dtype=np.float64)
+    m = work.size
+    if world <= 1:
+        return np.array([0, m], dtype=np.int64)
+    cum = np.concatenate([[0.0], np.cumsum(work + 1e-9)])
+    targets = cum[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(cum, targets, side="left")
+    b = np.concatenate([[0], inner, [m]]).astype(np.int64)
+    return np.maximum.accumulate(np.minimum(b, m))
+
+
+def owner_of(genes: np.ndarray, bounds: np.ndarray) -> np.ndarray:
+    """Rank owning each gene index under `bounds`."""
+    return (np.searchsorted(bounds, np.asarray(genes), side="right") - 1).astype(np.int64)
+
+
+def _all_gather_rows(local: np.ndarray, group):
+    import torch.distributed as dist
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, local, group=group)
+    return parts
+
+
+class _GeneStreams:
+    """sample() stand-in whose draws depend on (seed, gene) only, not on which rank owns the gene."""
+
+    def __init__(self, seed):
+        self.seed = int(seed) & 0x7fffffff
+
+    def __call__(self, kind, gene, n, size, count):
+        rng = np.random.default_rng([self.seed, int(gene)])
+        out = np.empty((count, size), dtype=np.int32)
+        for r in range(count):
+            if kind == "dense" or size == n:
+                out[r] = rng.permutation(n)[:size] + 1
+            else:
+                out[r] = rng.choice(n, size=size, replace=False, shuffle=True) + 1
+        return out
+
+
+def haystack_continuous_highD_sharded(x, expression, backend, grid_coord, *, group=None, scale=True,
+                                      weights_advanced_Q=None, randomization_count=100,
+                                      n_genes_to_randomize=100,
+                                      selection_method_genes_to_randomize="heavytails", spline_method="ns",
+                                      gene_names=None, seed=0, perm_source=None, cv_folds=None, row_stats=None,
+                                      src_rank=0):
+    """Gene-sharded haystack_continuous_highD (R/haystack_continuous.R:27-339) with a supplied grid.
+
+    backend: this rank's DeviceContext (or an object with the same compute methods).
+    Returns the same Haystack object on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    sparse_in = _sparse.is_sparse(expression)
+    if sparse_in:
+        expression = _sparse.as_RsparseMatrix(expression)
+    else:
+        expression = np.asarray(expression, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    if expression.shape[1] != x.shape[0]:
+        raise ValueError("The number of columns in 'expression' must be the same as the rows in 'x'")
+    if row_stats is not None:
+        expr_mean, expr_sd = (np.asarray(a, dtype=np.float64).copy() for a in row_stats)
+    else:
+        expr_mean, expr_sd = _hs.row_mean_sd(expression)
+    if expr_mean.size and np.nanmin(expr_mean) < 0:
+        raise ValueError("Some features have an average signal < 0. Expect average signal >= 0.")
+    keep = ~(expr_sd == 0)
+    if not keep.all():
+        expression = expression.row_subset(keep) if sparse_in else expression[keep]
+        if gene_names is not None:
+            gene_names = [g for g, k in zip(gene_names, keep) if k]
+    expr_mean = expr_mean[keep] + 1e-300
+    expr_sd = expr_sd[keep] + 1e-300
+    m, n = expression.shape
+    n_sel = min(int(n_genes_to_randomize), m)
+
+    center = sc = None
+    if scale:
+        x, center, sc = _hs.scale(x)
+    grid_coord = np.asarray(grid_coord, dtype=np.float64)
+
+    # ---- exchange step 1: density state from src_rank to everyone ----
+    dens = None
+    if rank == src_rank or world == 1:
+        dens = backend.density(x, grid_coord, w_q=weights_advanced_Q)
+    if world > 1:
+        backend.density_broadcast(n, grid_coord.shape[0], src=src_rank, group=group)
+
+    # ---- this rank's genes ----
+    work = np.diff(expression.p).astype(np.float64) if sparse_in else np.ones(m)
+    bounds = plan_gene_shards(work, world)
+    g0, g1 = int(bounds[rank]), int(bounds[rank + 1])
+    if sparse_in:
+        p = expression.p.astype(np.int64)
+        local = backend.dkl_csr(p[g0:g1 + 1] - p[g0], expression.j[p[g0]:p[g1]], expression.x[p[g0]:p[g1]])
+    else:
+        local = backend.dkl_dense(expression[g0:g1]) if g1 > g0 else np.zeros(0)
+    # ---- exchange step 2: gather D_KL ----
+    if world > 1:
+        d_kl = np.concatenate(_all_gather_rows(np.asarray(local, dtype=np.float64), group))
+    else:
+        d_kl = np.asarray(local, dtype=np.float64)
+
+    coeff_var = expr_sd / expr_mean
+    genes = _hs.select_genes_to_randomize(coeff_var, n_sel, selection_method_genes_to_randomize)
+    src = perm_source if perm_source is not None else _GeneStreams(seed)
+    owners = owner_of(genes, bounds)
+    mine = np.nonzero(owners == rank)[0]
+    rows_local = np.zeros((mine.size, randomization_count))
+    if mine.size:
+        if sparse_in:
+            vals, inds = [], []
+            for i in mine:
+                row = _sparse.extract_row_dgRMatrix_as_sparse(expression, int(genes[i]) + 1)
+                ids = src("sparse", int(genes[i]), n, row["val"].size, randomization_count)
+                vals.append(row["val"])
+                inds.append(np.asfortranarray(np.asarray(ids, dtype=np.int32).T))
+            rows_local = np.asarray(backend.dkl_perm_csr(vals, inds, index_base=1))
+        else:
+            for k, i in enumerate(mine):
+                perms = src("dense", int(genes[i]), n, n, randomization_count)
+                rows_local[k] = backend.dkl_perm_dense(expression[int(genes[i])],
+                                                       np.asfortranarray(np.asarray(perms, dtype=np.int32).T),
+                                                       index_base=1)
+    kld_rand = np.full((n_sel, randomization_count), np.nan)
+    if world > 1:
+        for idx, rows in _all_gather_rows((mine, rows_local), group):
+            kld_rand[idx] = rows
+    else:
+        kld_rand[mine] = rows_local
+
+    sets_mean, sets_sd = cv_folds if cv_folds is not None else (None, None)
+    pv = _fit.get_log_p_D_KL_continuous(d_kl, kld_rand, coeff_var, coeff_var[genes], spline_method=spline_method,
+                                        sets_mean=sets_mean, sets_sd=sets_sd, rng=np.random.default_rng(seed))
+    p_vals = pv["fitted"]
+    p_adjs = np.where(p_vals + math.log10(max(p_vals.size, 1)) > 0, 0.0, p_vals + math.log10(max(p_vals.size, 1)))
+    import pandas as pd
+    info = pv["info"]
+    info.update(method=spline_method, genes_to_randomize=genes + 1, KLD_rand=kld_rand)
+    results = pd.DataFrame({"D_KL": d_kl, "log.p.vals": p_vals, "log.p.adj": p_adjs},
+                           index=gene_names if gene_names is not None else None)
+    grid_out = grid_coord * sc + center if scale else grid_coord
+    return _hs.Haystack(results=results,
+                        info=dict(method="continuous_highD", randomization=info, grid_coordinates=grid_out,
+                                  coord_mean=center, coord_std=sc, cv=coeff_var, shard_bounds=bounds,
+                                  bandwidth=None if dens is None else dens["bandwidth"]))

@@ -104,3 +104,58 @@ def test_synthetic_csr_parity(ctx, n, d, g, m, rho):
         ids_d.append(np.asfortranarray(ids.T))
     want_r = ho.dkl_randomized_sparse(vals, ids_o, ref["density"], ref["Q"])
     assert _rel(ctx.dkl_perm_csr(vals, ids_d, index_base=1), want_r) < RTOL_DKL
+
+
+def test_sharded_layer_on_device(ctx, toy):
+    """The gene-sharded host layer with the real DeviceContext as backend (single rank here; the two-rank
+    logic is covered on CPU over gloo, the NCCL broadcast by bench.py --gpus N)."""
+    from singlecellhaystack_b200.distributed import haystack_continuous_highD_sharded
+    seed = int(toy["seed"])
+    expr = toy["expression"]
+    stats = ho.row_mean_sd(ho.RowSparse.from_dense(expr))
+    res = haystack_continuous_highD_sharded(
+        toy["coord"], sp.as_CsparseMatrix(expr), ctx, toy["grid100"], perm_source=synth.perm_source(seed),
+        row_stats=stats, cv_folds=(synth.cv_folds(seed, 0, 100), synth.cv_folds(seed, 1, 100)))
+    assert _rel(res["results"]["D_KL"].values, toy["dkl100"]) < RTOL_DKL
+    assert _rel(res["info"]["randomization"]["KLD_rand"], toy["full_KLD_rand"]) < RTOL_DKL
+    assert np.max(np.abs(res["results"]["log.p.vals"].values - toy["full_log_p"])) < ATOL_LOGP
+
+
+def test_density_buffers_roundtrip(ctx, toy):
+    """hs_density_buffers / hs_density_commit: a second context adopts the first one's resident state
+    (what the NCCL broadcast does between ranks) and scores identically."""
+    import torch
+    from singlecellhaystack_b200.device import DeviceContext, _wrap_device_ptr
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ctx.density(xs, toy["grid60"])
+    sp_ = ho.RowSparse.from_dense(toy["expression"])
+    want = ctx.dkl_csr(sp_.p, sp_.j, sp_.x)
+    with DeviceContext(0) as other:
+        d0, db, q0, qb = ctx.density_buffers(601, 60)
+        d1, db1, q1, qb1 = other.density_buffers(601, 60)
+        assert (db, qb) == (db1, qb1) and d0 != d1
+        dev = torch.device("cuda", 0)
+        ctx.synchronize()
+        _wrap_device_ptr(d1, db, dev).copy_(_wrap_device_ptr(d0, db, dev))
+        _wrap_device_ptr(q1, qb, dev).copy_(_wrap_device_ptr(q0, qb, dev))
+        torch.cuda.synchronize()
+        other.density_commit(601, 60)
+        assert other.shape == (601, 60)
+        np.testing.assert_array_equal(other.dkl_csr(sp_.p, sp_.j, sp_.x), want)
+
+
+def test_tensor_core_csr_rows_opt_in(ctx, monkeypatch):
+    """HS_UMMA_MIN_DENSITY routes the densest CSR rows through the tcgen05 scatter producer; same tolerance."""
+    n, d, g, m = 20000, 10, 100, 600
+    x, labels = synth.make_embedding(n, d)
+    xs, _, _ = synth.scale_coords(x)
+    grid = synth.make_grid(xs, g)
+    p, j, v = synth.make_csr_numpy(m, n, 0.15, labels)
+    ref = ho.density_stage(xs, grid)
+    want = ho.dkl_observed(ho.RowSparse(p=p, j=j, x=v, shape=(m, n)), ref["density"], ref["Q"])
+    ctx.density(xs, grid)
+    base = ctx.dkl_csr(p, j, v)
+    monkeypatch.setenv("HS_UMMA_MIN_DENSITY", "0.04")
+    got = ctx.dkl_csr(p, j, v)
+    assert _rel(base, want) < RTOL_DKL and _rel(got, want) < RTOL_DKL
+    assert not np.array_equal(got, base)          # the densest rows really took the other path
