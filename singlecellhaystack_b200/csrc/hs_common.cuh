@@ -71,7 +71,7 @@ struct hs_ctx {
   bool tiles_valid = false;    // the tiles match the resident density matrix
   DevBuf umma_flags;
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
-  DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, slab-bucketed ids / values
+  DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, slab-bucketed (id, value) pairs
   void* pinned = nullptr;      // small pinned host bounce buffer
   size_t pinned_cap = 0;
 };
@@ -111,7 +111,8 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
 // slab-staged sparse contraction (hs_spmm.cu); see there for the arguments
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out);
+                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out,
+                     const void* pairs_dev = nullptr);
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,

@@ -155,6 +155,7 @@ struct SpmmParams {
   Slots sl;
   const int32_t* cols;
   const float* vals;
+  const uint2* pairs;      // when set: interleaved (col, val bits) entries at coff (cols / vals unused)
   int col_base;            // 0 or 1 (R indices)
   const float* D;          // [N][ldD]
   int ldD;                 // multiple of 4
@@ -264,11 +265,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
       int lo = 0, hi = len;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if ((int64_t)p.cols[coff + mid] - p.col_base < c_begin) lo = mid + 1; else hi = mid;
+        const int cm = p.pairs ? (int)p.pairs[coff + mid].x : p.cols[coff + mid];
+        if ((int64_t)cm - p.col_base < c_begin) lo = mid + 1; else hi = mid;
       }
       pos = lo;
     }
-    if (pos < len) next_col = p.cols[coff + pos] - p.col_base;
+    if (pos < len) next_col = (p.pairs ? (int)p.pairs[coff + pos].x : p.cols[coff + pos]) - p.col_base;
   }
   float acc[K][4 * NV];
 #pragma unroll
@@ -277,6 +279,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
     for (int e = 0; e < 4 * NV; ++e) acc[k][e] = 0.f;
   const uint32_t scr = smem_u32(scratch + warp * 32);
   const bool atomic = p.n_seg > 1;
+  const bool paired = p.pairs != nullptr;
+  auto load_entry = [&](int64_t ci, int64_t vi, int& c, float& v) {
+    if (paired) {
+      const uint2 e = __ldg(p.pairs + ci);
+      c = (int)e.x;
+      v = __uint_as_float(e.y);
+    } else {
+      c = __ldg(p.cols + ci);
+      v = __ldg(p.vals + vi);
+    }
+  };
   // move the fp32 sums of the rows in `mask` into the fp64 column sums (one copy of the code)
   auto flush_rows = [&](unsigned mask) {
     while (mask) {
@@ -320,8 +333,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
       const int64_t co = __shfl_sync(0xffffffffu, coff, k0), vo = __shfl_sync(0xffffffffu, voff, k0);
       const int idx = __shfl_sync(0xffffffffu, pos, k0) + lane;
       if (idx < __shfl_sync(0xffffffffu, len, k0)) {
-        pf_c = __ldg(p.cols + co + idx);
-        pf_v = __ldg(p.vals + vo + idx);
+        load_entry(co + idx, vo + idx, pf_c, pf_v);
       }
     }
     if (warp == 0) {
@@ -356,16 +368,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
           // next batch: more of this row, or the first batch of the next active row of this slab
           if (n_in == 32) {
             if (idx + 32 < len_k) {
-              pf_c = __ldg(p.cols + co + idx + 32);
-              pf_v = __ldg(p.vals + vo + idx + 32);
+              load_entry(co + idx + 32, vo + idx + 32, pf_c, pf_v);
             }
           } else if (todo) {
             const int k2 = __ffs(todo) - 1;
             const int64_t co2 = __shfl_sync(0xffffffffu, coff, k2), vo2 = __shfl_sync(0xffffffffu, voff, k2);
             const int idx2 = __shfl_sync(0xffffffffu, pos, k2) + lane;
             if (idx2 < __shfl_sync(0xffffffffu, len, k2)) {
-              pf_c = __ldg(p.cols + co2 + idx2);
-              pf_v = __ldg(p.vals + vo2 + idx2);
+              load_entry(co2 + idx2, vo2 + idx2, pf_c, pf_v);
             }
           }
           // entries of this slab must form a prefix of the batch and none may lie before the slab
@@ -543,26 +553,43 @@ __global__ void k_perm_row_ptr(const int64_t* __restrict__ gp, int64_t n_sel, in
 __device__ __forceinline__ int div_magic(uint32_t id, uint64_t magic) { return (int)(((uint64_t)id * magic) >> 40); }
 
 constexpr int kSortUnroll = 8;   // independent loads in flight per thread
+constexpr int kSortMaxParts = 8;      // output-range parts per row (grid.y)
+constexpr int kSortPartItems = 32768; // target entries per part: 256 KB of pairs, so that the scatter
+                                      // windows of all resident CTAs stay in L2 until their sectors fill
 
+// Writes (id, value) pairs in slab order.  A row is split into up to kSortMaxParts contiguous bin ranges,
+// one CTA each: every CTA streams the whole row twice (histogram, scatter) but scatters only its own
+// range, into a window small enough to be L2-resident -- the single-range version wrote 16x the
+// algorithmic bytes to DRAM (one 32-byte sector per 4-byte store; profiles/r1_k4_perm_slab_sort_raw.csv).
 __global__ void __launch_bounds__(kSortThreads, 2)
 k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
                  const float* __restrict__ vals, const int32_t* __restrict__ ind, int index_base, int64_t N,
-                 uint64_t magic, int n_bins, int32_t* __restrict__ cols_out, float* __restrict__ vals_out) {
-  extern __shared__ unsigned int hist[];      // [n_bins + 1]; bin n_bins - 1 = overflow
+                 uint64_t magic, int n_bins, uint2* __restrict__ pairs_out) {
+  extern __shared__ unsigned int hist[];      // [bins of this part + 1]
   __shared__ unsigned int warp_tot[kSortThreads / 32];
-  const int64_t row = blockIdx.x;
+  __shared__ unsigned int before_tot;
+  // consecutive CTAs are the parts of one row: they run together and share the row's ids through L2
+  const int64_t row = blockIdx.x / kSortMaxParts;
   const int64_t s = row / n_perm;
   const int64_t beg = rp[row], nnz = rp[row + 1] - beg;
+  const int parts = (int)hs_max<int64_t>(1, hs_min<int64_t>(kSortMaxParts, (nnz + kSortPartItems - 1) / kSortPartItems));
+  const int part = blockIdx.x % kSortMaxParts;
+  if (part >= parts) return;
+  // bins [b_lo, b_hi) belong to this part; the last bin (n_bins - 1) collects invalid ids
+  const int b_lo = (int)((int64_t)n_bins * part / parts), b_hi = (int)((int64_t)n_bins * (part + 1) / parts);
+  const int nb = b_hi - b_lo;
   const int32_t* in = ind + beg;
   const float* vin = vals + gp[s];
   const int tid = threadIdx.x;
-  for (int i = tid; i <= n_bins; i += kSortThreads) hist[i] = 0u;
+  for (int i = tid; i <= nb; i += kSortThreads) hist[i] = 0u;
+  if (tid == 0) before_tot = 0u;
   __syncthreads();
   auto bin_of = [&](int32_t raw) {
     const int64_t id = (int64_t)raw - index_base;
     return (id < 0 || id >= N) ? n_bins - 1 : div_magic((uint32_t)id, magic);
   };
   constexpr int64_t kStep = (int64_t)kSortThreads * kSortUnroll;
+  unsigned int before = 0;
   for (int64_t i0 = 0; i0 < nnz; i0 += kStep) {
     int32_t raw[kSortUnroll];
 #pragma unroll
@@ -572,12 +599,20 @@ k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp,
     }
 #pragma unroll
     for (int u = 0; u < kSortUnroll; ++u)
-      if (i0 + (int64_t)u * kSortThreads + tid < nnz) atomicAdd(&hist[bin_of(raw[u])], 1u);
+      if (i0 + (int64_t)u * kSortThreads + tid < nnz) {
+        const int b = bin_of(raw[u]);
+        if (b < b_lo) ++before;
+        else if (b < b_hi) atomicAdd(&hist[b - b_lo], 1u);
+      }
   }
+  // entries in earlier parts
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if ((tid & 31) == 0 && before) atomicAdd(&before_tot, before);
   __syncthreads();
-  // exclusive scan of hist[0 .. n_bins): each thread owns a contiguous run
-  const int per = (n_bins + kSortThreads - 1) / kSortThreads;
-  const int lo = hs_min(tid * per, n_bins), hi = hs_min(lo + per, n_bins);
+  // exclusive scan of hist[0 .. nb): each thread owns a contiguous run
+  const int per = (nb + kSortThreads - 1) / kSortThreads;
+  const int lo = hs_min(tid * per, nb), hi = hs_min(lo + per, nb);
   unsigned int sum = 0;
   for (int i = lo; i < hi; ++i) sum += hist[i];
   unsigned int incl = sum;
@@ -589,7 +624,7 @@ k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp,
   }
   if (lane == 31) warp_tot[warp] = incl;
   __syncthreads();
-  unsigned int base = 0;
+  unsigned int base = before_tot;
   for (int w2 = 0; w2 < warp; ++w2) base += warp_tot[w2];
   unsigned int run = base + incl - sum;
   for (int i = lo; i < hi; ++i) {
@@ -598,28 +633,28 @@ k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp,
     run += c;
   }
   __syncthreads();
-  int32_t* co = cols_out + beg;
-  float* vo = vals_out + beg;
+  uint2* out = pairs_out + beg;
   for (int64_t i0 = 0; i0 < nnz; i0 += kStep) {
     int32_t raw[kSortUnroll];
-    float v[kSortUnroll];
 #pragma unroll
     for (int u = 0; u < kSortUnroll; ++u) {
       const int64_t i = i0 + (int64_t)u * kSortThreads + tid;
       raw[u] = i < nnz ? __ldg(in + i) : 0;
-      v[u] = i < nnz ? __ldg(vin + i) : 0.f;
     }
-    unsigned int at[kSortUnroll];
 #pragma unroll
-    for (int u = 0; u < kSortUnroll; ++u)
-      at[u] = (i0 + (int64_t)u * kSortThreads + tid < nnz) ? atomicAdd(&hist[bin_of(raw[u])], 1u) : 0u;
-#pragma unroll
-    for (int u = 0; u < kSortUnroll; ++u)
-      if (i0 + (int64_t)u * kSortThreads + tid < nnz) {
-        const int64_t id = (int64_t)raw[u] - index_base;
-        co[at[u]] = (id < 0 || id >= N) ? 0x7fffffff : (int32_t)id;
-        vo[at[u]] = v[u];
+    for (int u = 0; u < kSortUnroll; ++u) {
+      const int64_t i = i0 + (int64_t)u * kSortThreads + tid;
+      if (i < nnz) {
+        const int b = bin_of(raw[u]);
+        if (b >= b_lo && b < b_hi) {
+          // (storing the rank from the histogram pass instead of a second atomic was tried twice: the
+          // extra scattered 2-byte traffic costs more than the atomics save)
+          const unsigned int at = atomicAdd(&hist[b - b_lo], 1u);
+          const int64_t id = (int64_t)raw[u] - index_base;
+          out[at] = make_uint2((id < 0 || id >= N) ? 0x7fffffffu : (uint32_t)id, __float_as_uint(__ldg(vin + i)));
+        }
       }
+    }
   }
 }
 
@@ -641,7 +676,8 @@ int hs_slab_cells(const hs_ctx* ctx) {
 // chain the order-independent fallback without a host round trip.
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out) {
+                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out,
+                     const void* pairs_dev) {
   const int64_t n_rows = perm ? n_units * (int64_t)n_perm : n_units;
   if (n_rows <= 0) return HS_OK;
   if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many rows (%lld) for one call", (long long)n_rows);
@@ -743,6 +779,7 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   prm.sl = sl;
   prm.cols = cols_dev;
   prm.vals = vals_dev;
+  prm.pairs = (const uint2*)pairs_dev;
   prm.col_base = col_base;
   prm.D = (const float*)ctx->D32.p;
   prm.ldD = ldD;
@@ -798,18 +835,17 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
   if (smem > 200 * 1024) return -1;
   const int64_t n_ids = n_vals_total * n_perm;
   HS_TRY(hs_ensure(ctx, ctx->perm_rp, sizeof(int64_t) * (size_t)(n_rows + 1)));
-  HS_TRY(hs_ensure(ctx, ctx->perm_cols, sizeof(int32_t) * (size_t)hs_max<int64_t>(n_ids, 1)));
-  HS_TRY(hs_ensure(ctx, ctx->perm_vals, sizeof(float) * (size_t)hs_max<int64_t>(n_ids, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->perm_cols, sizeof(uint2) * (size_t)hs_max<int64_t>(n_ids, 1)));   // (id, value) pairs
   cudaStream_t st = ctx->stream;
   int64_t* rp = (int64_t*)ctx->perm_rp.p;
   k_perm_row_ptr<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(gene_ptr_dev, n_sel, n_perm, rp);
   HS_LAUNCH_CHECK(ctx);
   HS_CUDA(ctx, cudaFuncSetAttribute(k_perm_slab_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uint64_t magic = ((1ull << 40) + (uint64_t)S - 1) / (uint64_t)S;
-  k_perm_slab_sort<<<(unsigned)n_rows, kSortThreads, smem, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base,
-                                                                 ctx->N, magic, n_bins, (int32_t*)ctx->perm_cols.p,
-                                                                 (float*)ctx->perm_vals.p);
+  if (n_rows * kSortMaxParts > 0x7fffffffLL) return -1;
+  k_perm_slab_sort<<<(unsigned)(n_rows * kSortMaxParts), kSortThreads, smem, st>>>(
+      rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base, ctx->N, magic, n_bins, (uint2*)ctx->perm_cols.p);
   HS_LAUNCH_CHECK(ctx);
-  return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, (const int32_t*)ctx->perm_cols.p, (const float*)ctx->perm_vals.p, 0,
-                          out_dev, n_perm, n_sel, /*allow_umma=*/false, nullptr);   // ids are only slab-sorted
+  return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
+                          /*allow_umma=*/false /* ids are only slab-sorted */, nullptr, ctx->perm_cols.p);
 }
