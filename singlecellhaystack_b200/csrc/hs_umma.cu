@@ -223,6 +223,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams p) {
   constexpr bool PERM = MODE == kModePerm;
   constexpr int kStages = MODE == kModeCsr ? kStagesCsr : kStagesDense;
+  // dense mode uses the two otherwise idle warps (6, 7) as extra producers
+  constexpr int kProducerWarps = MODE == kModeDense ? 6 : 4;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand stages (swizzle atoms), then barriers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full_a(s), 4);
+      mbar_init(full_a(s), kProducerWarps);
       mbar_init(full_b(s), 1);
       mbar_init(empty(s), 1);
     }
@@ -263,7 +265,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 4 || (MODE == kModeDense && (warp == 6 || warp == 7))) {
     // ================= A producers =================
     bool over = false;
     if (MODE == kModeCsr) {
@@ -404,28 +406,55 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
       const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kTileBytes;
       const int64_t c0 = (kb_begin + i) * kBK;
       if (!PERM) {
-        // task = (row group of 8, cell): lanes 0-15 cover 128 rows of one cell, 16-31 the next cell
+        // task = (row group of 8, cell): lanes 0-15 cover 128 rows of one cell, 16-31 the next cell.
+        // 192 producer threads, 5-6 tasks each.  All of a stage's loads are issued before the first
+        // conversion (one memory round trip per stage instead of one per task), and the lines the stage
+        // four steps ahead will read are prefetched into L2 so that the round trip is an L2 hit.
+        const int pt = (warp < 4 ? warp : warp - 2) * 32 + lane;            // 0..191
         const bool vec = ((p.ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.E) & 15) == 0);
-#pragma unroll 2
-        for (int t = threadIdx.x; t < 1024; t += 128) {
+        constexpr int kMaxTasks = (1024 + 191) / 192;                        // 6
+        float4 bu[kMaxTasks], bw[kMaxTasks];
+        {
+          const int64_t pc0 = c0 + 4 * kBK;
+#pragma unroll
+          for (int q = 0; q < kMaxTasks; ++q) {
+            const int t = pt + 192 * q;
+            const int64_t cell = pc0 + (t >> 4), r = row0 + 8 * (t & 15);
+            if (t < 1024 && cell < p.N && r < p.n_rows && (lane & 3) == 0)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.E + r + cell * p.ld));
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < kMaxTasks; ++q) {
+          const int t = pt + 192 * q;
           const int mg = t & 15, k = t >> 4;
           const int64_t cell = c0 + k, r = row0 + 8 * mg;
-          float x[8];
-          if (cell < p.N && r + 8 <= p.n_rows && vec) {
-            const float4 u = __ldg(reinterpret_cast<const float4*>(p.E + r + cell * p.ld));
-            const float4 w = __ldg(reinterpret_cast<const float4*>(p.E + r + 4 + cell * p.ld));
-            x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = w.x; x[5] = w.y; x[6] = w.z; x[7] = w.w;
-          } else {
+          bu[q] = bw[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (t < 1024 && cell < p.N) {
+            if (r + 8 <= p.n_rows && vec) {
+              bu[q] = __ldg(reinterpret_cast<const float4*>(p.E + r + cell * p.ld));
+              bw[q] = __ldg(reinterpret_cast<const float4*>(p.E + r + 4 + cell * p.ld));
+            } else {
+              float x[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = (cell < p.N && r + e < p.n_rows) ? __ldg(p.E + r + e + cell * p.ld) : 0.f;
+              for (int e = 0; e < 8; ++e) x[e] = (r + e < p.n_rows) ? __ldg(p.E + r + e + cell * p.ld) : 0.f;
+              bu[q] = make_float4(x[0], x[1], x[2], x[3]);
+              bw[q] = make_float4(x[4], x[5], x[6], x[7]);
+            }
           }
+        }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] *= kScaleA;
-          uint4 hi, lo;
-          over |= split8(x, hi, lo);
-          const uint32_t off = chunk_off(mg, k);
-          sts_u4(a_hi + off, hi);
-          sts_u4(a_lo + off, lo);
+        for (int q = 0; q < kMaxTasks; ++q) {
+          const int t = pt + 192 * q;
+          if (t < 1024) {
+            const float x[8] = {bu[q].x * kScaleA, bu[q].y * kScaleA, bu[q].z * kScaleA, bu[q].w * kScaleA,
+                                bw[q].x * kScaleA, bw[q].y * kScaleA, bw[q].z * kScaleA, bw[q].w * kScaleA};
+            uint4 hi, lo;
+            over |= split8(x, hi, lo);
+            const uint32_t off = chunk_off(t & 15, t >> 4);
+            sts_u4(a_hi + off, hi);
+            sts_u4(a_lo + off, lo);
+          }
         }
       } else {
         // task = (row group of 8, cell): lanes run over 32 consecutive cells (coalesced index loads)
