@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--e2e-genes", type=int, default=0, help="0 = all genes if host memory allows")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the side measurement of the dense (tcgen05) kernel")
+    ap.add_argument("--dense-genes", type=int, default=1024)
     ap.add_argument("--cpu-genes", type=int, default=24)
     ap.add_argument("--cpu-perms", type=int, default=8)
     ap.add_argument("--cpu-density-cells", type=int, default=50_000)
@@ -438,6 +440,11 @@ def run_b200(a):
                 "traffic": _ncu_traffic(), "kernel": "k_slab_spmm (hs_dkl_csr_dev: slab-staged CSR contraction + KL epilogue)", "kernel_ms": k3_ms,
                 "algorithmic_bytes": k3_bytes, "peak_source": peak_src}
 
+    # ---- side measurement: the dense contraction (K2, tcgen05) on the same density state ----
+    dense_extra = None
+    if rank == 0 and world == 1 and not a.no_dense and g <= 128:
+        dense_extra = run_dense_side(a, ctx, dev, peak)
+
     # ---- end to end through the host-pointer C ABI (pinned host inputs, H2D inside the timed region) ----
     e2e = None
     if not a.no_e2e:
@@ -466,6 +473,8 @@ def run_b200(a):
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if dense_extra is not None:
+            line["extra"] = {"k2_dense_tcgen05": dense_extra}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if parity is not None:
@@ -474,6 +483,37 @@ def run_b200(a):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_dense_side(a, ctx, dev, hbm_peak):
+    """K2 (dense expression, tensor cores) on a device-resident fp32 matrix of --dense-genes genes x all cells;
+    not part of `value` (the headline workload is sparse), reported so the dense kernel has a number."""
+    import torch
+    m, n, g = a.dense_genes, a.cells, a.grid_points
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1)
+    e = torch.rand((n, m), device=dev, generator=gen)                  # (cells, genes) == genes x cells column-major
+    e = torch.where(e < 0.1, torch.log1p(1 + 20 * e), torch.zeros_like(e)).contiguous()
+    out = torch.empty(m, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        ctx.dkl_dense_dev(e, m, m, out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 5
+    for _ in range(reps):
+        ctx.dkl_dense_dev(e, m, m, out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbs = 4.0 * n * m / (ms * 1e-3) / 1e9
+    del e
+    torch.cuda.empty_cache()
+    return {"genes": m, "cells": n, "ms": ms, "genes_per_s": m / (ms * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "algorithmic_bytes": 4.0 * n * m},
+            "mma_tflops_issued": 3 * 2.0 * n * m * 128 / (ms * 1e-3) / 1e12,
+            "note": "fp32 expression, 3 fp16 MMAs per K step (hi/lo split operands), N padded to 128; includes the KL epilogue"}
 
 
 def _ncu_traffic():

@@ -332,7 +332,7 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   HS_TRY(hs_ensure(ctx, ctx->cols32, sizeof(int32_t) * (size_t)hs_max<int64_t>(n_ids, 1)));
   HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)hs_max<int64_t>(n_vals, 1)));
   const size_t stage_vals = (size_t)hs_min<int64_t>((int64_t)chunk, hs_max<int64_t>(n_vals, 1));
-  for (int b = 0; b < 2; ++b) HS_TRY(hs_ensure(ctx, ctx->stage_x[b], sizeof(double) * stage_vals));
+  HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * stage_vals));
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
 
   // row pointers rebased to the uploaded arrays
@@ -343,37 +343,52 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
   HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));
 
-  ScopedTimer tcopy(ctx, HS_T_COPY);
-  // values: staged fp64 -> fp32
-  int k = 0;
-  for (int64_t off = 0; off < n_vals; off += (int64_t)stage_vals, ++k) {
-    const int b = k & 1;
-    const int64_t n = hs_min<int64_t>((int64_t)stage_vals, n_vals - off);
-    if (k >= 2) HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[b], 0));
-    HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[b].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
-    HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], cs));
-    HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[b], 0));
-    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, (float*)ctx->vals32.p + off, n));
-    HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+  // Uploads (and the fp64 -> fp32 conversion of the values) run on the copy stream; the contraction of a
+  // piece of rows starts on the compute stream as soon as that piece has landed, so PCIe transfer and
+  // scoring overlap.  A piece holds enough rows to fill the machine; the permutation form is one piece
+  // (its output block is batch-local).
+  std::vector<int64_t> piece_end;
+  if (!perm) {
+    const int64_t min_rows = (int64_t)ctx->sm_count * 32;
+    const int64_t target_vals = hs_max<int64_t>(n_vals / 8, (int64_t)32 << 20);
+    int64_t u0 = 0;
+    while (u0 < n_units) {
+      int64_t u1 = hs_min<int64_t>(n_units, u0 + min_rows);
+      while (u1 < n_units && rel[u1] - rel[u0] < target_vals) ++u1;
+      if (n_units - u1 < min_rows) u1 = n_units;
+      piece_end.push_back(u1);
+      u0 = u1;
+    }
+  } else {
+    piece_end.push_back(n_units);
   }
-  // ids: straight into place, in pieces so that pageable sources do not serialise one huge copy
-  const int64_t piece = (int64_t)64 << 20;
-  for (int64_t off = 0; off < n_ids; off += piece) {
-    const int64_t n = hs_min<int64_t>(piece, n_ids - off);
-    HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 * ipv + off, sizeof(int32_t) * (size_t)n,
-                                 cudaMemcpyHostToDevice, cs));
-  }
-  HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[0], cs));
-  HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[0], 0));
-  tcopy.stop();
-
   ScopedTimer tm(ctx, timer_slot);
-  if (perm)
-    HS_TRY(hs_run_perm_csr(ctx, (const int64_t*)ctx->ptrs.p, n_units, n_vals, (const float*)ctx->vals32.p,
-                           (const int32_t*)ctx->cols32.p, n_perm, index_base, dev_out));
-  else
-    HS_TRY(hs_run_csr(ctx, (const int64_t*)ctx->ptrs.p, (const int32_t*)ctx->cols32.p, (const float*)ctx->vals32.p,
-                      n_units, dev_out));
+  const int64_t id_piece = (int64_t)64 << 20;
+  int64_t u0 = 0;
+  for (size_t pc = 0; pc < piece_end.size(); ++pc) {
+    const int64_t u1 = piece_end[pc];
+    const int64_t a0 = rel[u0], a1 = rel[u1];
+    for (int64_t off = a0; off < a1; off += (int64_t)stage_vals) {
+      const int64_t n = hs_min<int64_t>((int64_t)stage_vals, a1 - off);
+      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
+      HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p + off, n, cs));
+    }
+    // ids: straight into place, in pieces so that pageable sources do not serialise one huge copy
+    for (int64_t off = a0 * ipv; off < a1 * ipv; off += id_piece) {
+      const int64_t n = hs_min<int64_t>(id_piece, a1 * ipv - off);
+      HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 * ipv + off, sizeof(int32_t) * (size_t)n,
+                                   cudaMemcpyHostToDevice, cs));
+    }
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[0], cs));
+    HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[0], 0));
+    if (perm)
+      HS_TRY(hs_run_perm_csr(ctx, (const int64_t*)ctx->ptrs.p, n_units, n_vals, (const float*)ctx->vals32.p,
+                             (const int32_t*)ctx->cols32.p, n_perm, index_base, dev_out));
+    else
+      HS_TRY(hs_run_csr(ctx, (const int64_t*)ctx->ptrs.p + u0, (const int32_t*)ctx->cols32.p,
+                        (const float*)ctx->vals32.p, u1 - u0, dev_out + u0));
+    u0 = u1;
+  }
   tm.stop();
   return HS_OK;
 }
@@ -475,7 +490,7 @@ int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, d
                                    sizeof(double) * n_genes, (size_t)nc, cudaMemcpyHostToDevice, cs));
     HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], cs));
     HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[b], 0));
-    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, (float*)ctx->dense32.p + c0 * n_genes, nc * n_genes));
+    HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[b].p, (float*)ctx->dense32.p + c0 * n_genes, nc * n_genes, st));
     HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
   }
   ScopedTimer tm(ctx, HS_T_DENSE);
@@ -499,7 +514,7 @@ int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_p
   HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, v, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
   HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_j[0].p, perm, sizeof(int32_t) * (size_t)N * n_perm,
                                cudaMemcpyHostToDevice, st));
-  HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p, N));
+  HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p, N, st));
   ScopedTimer tm(ctx, HS_T_PERM);
   HS_TRY(hs_run_perm_dense(ctx, (const float*)ctx->vals32.p, (const int32_t*)ctx->stage_j[0].p, n_perm,
                            index_base, (double*)ctx->out.p));

@@ -129,7 +129,7 @@ int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
                       int index_base, double* out_dev);
-int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n);
+int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n, cudaStream_t stream);
 
 #ifdef __CUDACC__
 // ---- device helpers -----------------------------------------------------------------------

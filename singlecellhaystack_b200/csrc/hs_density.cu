@@ -212,10 +212,10 @@ __global__ void k_f64_to_f32(const double* __restrict__ src, float* __restrict__
 
 }  // namespace
 
-int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n) {
+int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n, cudaStream_t stream) {
   if (n <= 0) return HS_OK;
   const int blocks = (int)hs_min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
-  k_f64_to_f32<<<blocks, 256, 0, ctx->stream>>>(src, dst, n);
+  k_f64_to_f32<<<blocks, 256, 0, stream>>>(src, dst, n);
   HS_LAUNCH_CHECK(ctx);
   return HS_OK;
 }
