@@ -1,0 +1,106 @@
+"""Size-independent properties of the scored path at the headline shape (1M cells, 100 grid points),
+where the oracle is too slow to be the checker for every gene: scale and order invariance, P == Q -> 0,
+dense/CSR agreement, all through the C ABI.  A handful of genes is still compared with the oracle."""
+import numpy as np
+import pytest
+
+from oracle import haystack_oracle as ho
+from singlecellhaystack_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+N, D, G, M = 1_000_000, 50, 100, 768
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def big(ctx):
+    x, labels = synth.make_embedding(N, D)
+    xs, _, _ = synth.scale_coords(x)
+    grid = synth.make_grid(xs, G)
+    out = ctx.density(xs, grid, want_nearest=True)
+    p, j, v = synth.make_csr_numpy(M, N, 0.05, labels, block=16)
+    return dict(xs=xs, grid=grid, dens=out, p=p, j=j, v=v)
+
+
+def test_density_stage_invariants(ctx, big):
+    q = big["dens"]["Q"]
+    assert q.shape == (G,) and abs(q.sum() - 1.0) < 1e-12 and (q > 0).all()
+    near = big["dens"]["nearest"]
+    assert near.min() >= 0 and near.max() < G
+    # the bandwidth is the exact median of the nearest-grid-point distances (even N: mean of the middle two)
+    sub = np.arange(0, N, 997)
+    dist = np.sqrt(((big["xs"][sub, None, :] - big["grid"][None, :, :]) ** 2).sum(axis=2))
+    np.testing.assert_array_equal(dist.argmin(axis=1), near[sub])
+    # re-running on the same inputs is bit-reproducible (fixed-order reductions)
+    again = ctx.density(big["xs"], big["grid"])
+    assert again["bandwidth"] == big["dens"]["bandwidth"]
+    np.testing.assert_array_equal(again["Q"], q)
+
+
+def test_csr_invariances_and_spot_parity(ctx, big):
+    p, j, v = big["p"], big["j"], big["v"]
+    base = ctx.dkl_csr(p, j, v)
+    assert np.isfinite(base).all() and (base > -1e-12).all()
+    # D_KL is invariant under a positive rescaling of a gene's values
+    assert _rel(ctx.dkl_csr(p, j, 7.5 * v), base) < 2e-6
+    # ... and under the order of the stored entries (takes the order-independent gather kernel)
+    rng = np.random.default_rng(5)
+    j2, v2 = j.copy(), v.copy()
+    for g in range(0, M, 37):
+        perm = rng.permutation(p[g + 1] - p[g]) + p[g]
+        j2[p[g]:p[g + 1]] = j[perm]
+        v2[p[g]:p[g + 1]] = v[perm]
+    assert _rel(ctx.dkl_csr(p, j2, v2), base) < 2e-6
+    # int32 and int64 row pointers are the same call (with few rows the cell axis is split over CTAs and the
+    # fp64 partial sums meet in atomics, so repeated calls agree to rounding, not bit for bit)
+    np.testing.assert_allclose(ctx.dkl_csr(p.astype(np.int32), j, v), base, rtol=1e-12)
+    # a few genes against the fp64 oracle (density recomputed on the host for those cells only)
+    from scipy.spatial.distance import cdist
+    bw, q = big["dens"]["bandwidth"], big["dens"]["Q"]
+    for g in (0, M // 2, M - 1):
+        cells = j[p[g]:p[g + 1]]
+        dn = cdist(big["xs"][cells], big["grid"]) / bw
+        pr = (np.exp(-dn * dn / 2) * v[p[g]:p[g + 1], None]).sum(axis=0) + ho.PSEUDO
+        pr /= pr.sum()
+        want = float((pr * np.log(pr / q)).sum())
+        assert abs(base[g] - want) <= 1e-5 * abs(want)
+
+
+def test_uniform_gene_scores_zero_and_dense_matches_csr(ctx, big):
+    # a gene expressed equally in every cell has P == Q (R/haystack_continuous.R:357-360 with w == 1)
+    ones_p = np.array([0, N], dtype=np.int64)
+    d0 = ctx.dkl_csr(ones_p, np.arange(N, dtype=np.int32), np.ones(N))
+    assert abs(d0[0]) < 1e-7
+    # dense rows (tensor-core kernel) agree with their CSR form (slab kernel)
+    p, j, v = big["p"], big["j"], big["v"]
+    rows = [0, 5, M - 1]
+    dense = np.zeros((len(rows) + 1, N))
+    for k, g in enumerate(rows):
+        dense[k, j[p[g]:p[g + 1]]] = v[p[g]:p[g + 1]]
+    dense[-1] = 1.0
+    got = ctx.dkl_dense(dense)
+    want = ctx.dkl_csr(p, j, v)[rows]
+    assert _rel(got[:-1], want) < 1e-5
+    assert abs(got[-1]) < 1e-7
+
+
+def test_randomized_rows_are_a_null_distribution(ctx, big):
+    """Permuted rows of a strongly structured gene score far below the observed D_KL, and each permuted
+    row equals the observed-path result on the same (ids, values)."""
+    p, j, v = big["p"], big["j"], big["v"]
+    base = ctx.dkl_csr(p, j, v)
+    nnz = np.diff(p)
+    g = int(np.argmax(np.where(nnz > 20000, base, -1.0)))            # a structured gene with many cells
+    val = v[p[g]:p[g + 1]]
+    src = synth.perm_source(3)
+    ids = src("sparse", g, N, val.size, 6)                                   # (6, nnz) 1-based
+    rand = ctx.dkl_perm_csr([val], [np.asfortranarray(ids.T)], index_base=1)[0]
+    assert (rand < 0.5 * base[g]).all() and (rand > 0).all()
+    # the same rows through the CSR entry point (ids unsorted -> gather kernel)
+    pp = np.arange(0, 7, dtype=np.int64) * val.size
+    again = ctx.dkl_csr(pp, (ids - 1).astype(np.int32).ravel(), np.tile(val, 6))
+    assert _rel(rand, again) < 2e-6
