@@ -19,6 +19,7 @@
 // then runs the order-independent gather kernel (hs_contract.cu) instead.
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "hs_common.cuh"
@@ -513,7 +514,7 @@ int launch_spmm(hs_ctx* ctx, const SpmmParams& prm, int n_tiles, size_t smem) {
 // Tile shapes (rows per warp K, warps per CTA W) per float4-per-lane count NV, smallest first.
 // 4*NV*K accumulator registers per thread: W = 16 allows 128 registers, W = 12 allows 168.
 struct Shape { int k, w; };
-const Shape kShapes1[] = {{1, 16}, {2, 16}, {4, 16}, {8, 16}, {17, 12}};
+const Shape kShapes1[] = {{1, 16}, {2, 16}, {4, 16}, {8, 16}, {13, 16}, {17, 12}};   // (11,20), (9,24) measured slower
 const Shape kShapes2[] = {{1, 16}, {2, 16}, {4, 16}, {8, 12}};
 const Shape kShapes4[] = {{1, 16}, {2, 16}, {4, 12}};
 const Shape kShapes8[] = {{1, 16}, {2, 12}};
@@ -521,7 +522,13 @@ const Shape kShapes8[] = {{1, 16}, {2, 12}};
 // smallest shape whose single wave of `sms` CTAs covers n_rows; the largest one otherwise
 Shape pick_shape(int nv, int64_t n_rows, int sms) {
   const Shape* t = nv == 1 ? kShapes1 : nv == 2 ? kShapes2 : nv == 4 ? kShapes4 : kShapes8;
-  const int n = nv == 1 ? 5 : nv == 2 ? 4 : nv == 4 ? 3 : 2;
+  const int n = nv == 1 ? 6 : nv == 2 ? 4 : nv == 4 ? 3 : 2;
+  if (const char* e = getenv("HS_SLAB_SHAPE")) {      // "k,w": tuning experiments
+    int k = 0, w = 0;
+    if (sscanf(e, "%d,%d", &k, &w) == 2)
+      for (int i = 0; i < n; ++i)
+        if (t[i].k == k && t[i].w == w) return t[i];
+  }
   for (int i = 0; i < n; ++i)
     if ((int64_t)t[i].k * t[i].w * sms >= n_rows) return t[i];
   return t[n - 1];
@@ -794,7 +801,7 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
 #define HS_SPMM_CASE(NVv, Kv, Wv) \
   if (n_sub <= 0) {} else \
   if (NV == NVv && K == Kv && kWarps == Wv) { HS_TRY((launch_spmm<NVv, Kv, Wv>(ctx, prm, n_tiles, smem))); } else
-  HS_SPMM_CASE(1, 1, 16) HS_SPMM_CASE(1, 2, 16) HS_SPMM_CASE(1, 4, 16) HS_SPMM_CASE(1, 8, 16) HS_SPMM_CASE(1, 17, 12)
+  HS_SPMM_CASE(1, 1, 16) HS_SPMM_CASE(1, 2, 16) HS_SPMM_CASE(1, 4, 16) HS_SPMM_CASE(1, 8, 16) HS_SPMM_CASE(1, 13, 16) HS_SPMM_CASE(1, 17, 12)
   HS_SPMM_CASE(2, 1, 16) HS_SPMM_CASE(2, 2, 16) HS_SPMM_CASE(2, 4, 16) HS_SPMM_CASE(2, 8, 12)
   HS_SPMM_CASE(4, 1, 16) HS_SPMM_CASE(4, 2, 16) HS_SPMM_CASE(4, 4, 12)
   HS_SPMM_CASE(8, 1, 16) HS_SPMM_CASE(8, 2, 12)
