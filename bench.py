@@ -359,12 +359,47 @@ def run_b200(a):
     else:
         cv = cv_local
     sel = hs_host.select_genes_to_randomize(cv, min(a.rand_genes, m_total), "heavytails")   # global 0-based
-    # units = (selected gene, permutation block); a gene's blocks stay on the rank that owns the row
-    owner = sel // m_local
-    mine = np.nonzero(owner == rank)[0]
-    sel_local = (sel[mine] - rank * m_local).astype(np.int64)
-    gene_ptr, pval, pind, r_loc = make_perm_inputs_device(a, p.cpu().numpy(), vals, sel_local, sel[mine], 0,
-                                                          a.rand_count, dev)
+    p_host = p.cpu().numpy()
+    if world == 1:
+        sel_local = sel.astype(np.int64)
+        gene_ptr, pval, pind, r_loc = make_perm_inputs_device(a, p_host, vals, sel_local, sel, 0, a.rand_count, dev)
+        mine = np.arange(len(sel))
+    else:
+        # units = (selected gene, block of permutations), dealt to ranks by descending cost (LPT) so that the
+        # fixed total of S x R permuted rows is balanced; the selected rows' values are exchanged once
+        # during set-up (inputs: ~100 rows), the indices are generated where they are used.
+        owner = sel // m_local
+        own = [(int(gid), vals[int(p_host[gid - rank * m_local]):int(p_host[gid - rank * m_local + 1])].cpu().numpy())
+               for gid in sel[owner == rank]]
+        rows_all = [None] * world
+        dist.all_gather_object(rows_all, own)
+        row_vals = {gid: v for part in rows_all for gid, v in part}
+        n_blocks = 4 if a.rand_count % 4 == 0 else 1
+        r_loc = a.rand_count // n_blocks
+        units = sorted(((len(row_vals[int(gid)]), int(gid), b) for gid in sel for b in range(n_blocks)), reverse=True)
+        load = np.zeros(world)
+        mine_units = []
+        for cost, gid, b in units:
+            r = int(np.argmin(load))
+            load[r] += cost
+            if r == rank:
+                mine_units.append((gid, b))
+        gp = [0]
+        val_parts, ind_parts = [], []
+        from singlecellhaystack_b200 import synth
+        for gid, b in mine_units:
+            v = torch.as_tensor(row_vals[gid], device=dev)
+            nnz_g = int(v.numel())
+            gp.append(gp[-1] + nnz_g)
+            val_parts.append(v)
+            idx = torch.arange(nnz_g, device=dev, dtype=torch.int64)[None, :].expand(r_loc, nnz_g)
+            stream = (gid * 100003 + torch.arange(b * r_loc, (b + 1) * r_loc, device=dev, dtype=torch.int64))[:, None].expand(r_loc, nnz_g)
+            ids = synth.feistel_perm(synth.BASE_SEED, stream.contiguous(), idx.contiguous(), a.cells)
+            ind_parts.append(ids.to(torch.int32).reshape(-1))
+        gene_ptr = torch.tensor(gp, dtype=torch.int64, device=dev)
+        pval = torch.cat(val_parts).contiguous() if val_parts else torch.zeros(0, dtype=torch.float32, device=dev)
+        pind = torch.cat(ind_parts).contiguous() if ind_parts else torch.zeros(0, dtype=torch.int32, device=dev)
+        mine = np.arange(len(mine_units))
     n_sel_local = len(mine)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
@@ -467,8 +502,8 @@ def run_b200(a):
                        "rand_count": a.rand_count, "l2": "inputs (CSR %.1f GB) larger than L2" % (8.0 * nnz / 1e9),
                        "setup_s": round(setup_s, 1),
                        "parallelism": ("1 process per GPU, gene-sharded (30k genes each); K1 on rank 0 + NCCL broadcast of the "
-                                       "density state; the 100 x 100 randomized rows are a fixed total split over the ranks "
-                                       "that own the selected genes") if world > 1 else "1 GPU"},
+                                       "density state; the S x R randomized rows are a fixed total, dealt to the ranks as "
+                                       "(gene, 25-permutation) units balanced by nnz") if world > 1 else "1 GPU"},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
         }
         if e2e is not None:
