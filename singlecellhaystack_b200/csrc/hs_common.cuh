@@ -124,8 +124,10 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
                       const int32_t* perm_dev, int index_base, int64_t n_rows, double* out_dev,
                       const int** flag_dev_out);
 bool hs_umma_disabled();   // HS_DISABLE_UMMA=1 forces the SIMT kernels (A/B comparisons)
+int hs_csr_umma_segments(const hs_ctx* ctx, int64_t n_dense);   // cell segments hs_run_csr_umma will use
 int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
-                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP, int* flags);
+                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP,
+                    int64_t seg_stride, int n_seg, int* flags);
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
                       int index_base, double* out_dev);

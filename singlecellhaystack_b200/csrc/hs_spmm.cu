@@ -164,31 +164,27 @@ struct SpmmParams {
   int slab_cells;          // S
   int64_t seg_cells;       // cells per grid.y segment (multiple of S)
   int n_seg;
-  double* P64;             // [n_rows][ldP] fp64 column sums (zeroed by the caller)
+  double* P64;             // [n_seg][n_rows][ldP] fp64 column sums (zeroed by the caller); a (segment, row)
+                           // has exactly one writer, and the epilogue adds the segments in a fixed order
+  int64_t seg_stride;      // doubles between the segments of P64
   int ldP;
   int* flags;              // bit 0: order violation / negative id -> caller falls back
 };
 
 template <int NV, int K>
-__device__ __forceinline__ void flush_row(float (&acc)[4 * NV], double* __restrict__ prow, int lane, int ldD,
-                                          bool atomic) {
+__device__ __forceinline__ void flush_row(float (&acc)[4 * NV], double* __restrict__ prow, int lane, int ldD) {
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int c0 = 4 * (lane + 32 * v);
     if (c0 < ldD) {
-      if (atomic) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) atomicAdd(prow + c0 + e, (double)acc[4 * v + e]);
-      } else {
-        double2 a = *reinterpret_cast<double2*>(prow + c0);
-        double2 b = *reinterpret_cast<double2*>(prow + c0 + 2);
-        a.x += (double)acc[4 * v + 0];
-        a.y += (double)acc[4 * v + 1];
-        b.x += (double)acc[4 * v + 2];
-        b.y += (double)acc[4 * v + 3];
-        *reinterpret_cast<double2*>(prow + c0) = a;
-        *reinterpret_cast<double2*>(prow + c0 + 2) = b;
-      }
+      double2 a = *reinterpret_cast<double2*>(prow + c0);
+      double2 b = *reinterpret_cast<double2*>(prow + c0 + 2);
+      a.x += (double)acc[4 * v + 0];
+      a.y += (double)acc[4 * v + 1];
+      b.x += (double)acc[4 * v + 2];
+      b.y += (double)acc[4 * v + 3];
+      *reinterpret_cast<double2*>(prow + c0) = a;
+      *reinterpret_cast<double2*>(prow + c0 + 2) = b;
     }
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[4 * v + e] = 0.f;
@@ -279,7 +275,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
 #pragma unroll
     for (int e = 0; e < 4 * NV; ++e) acc[k][e] = 0.f;
   const uint32_t scr = smem_u32(scratch + warp * 32);
-  const bool atomic = p.n_seg > 1;
+  double* const P64 = p.P64 + (int64_t)blockIdx.y * p.seg_stride;   // this segment's sums
   const bool paired = p.pairs != nullptr;
   auto load_entry = [&](int64_t ci, int64_t vi, int& c, float& v) {
     if (paired) {
@@ -307,7 +303,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
           }
         }
       const int row_k = __shfl_sync(0xffffffffu, row, k);
-      flush_row<NV, K>(tmp, p.P64 + (int64_t)row_k * p.ldP, lane, ldD, atomic);
+      flush_row<NV, K>(tmp, P64 + (int64_t)row_k * p.ldP, lane, ldD);
     }
   };
   bool violation = false;
@@ -472,15 +468,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
   // ---------------- final flush, left-over (out of range) ids ----------------
   flush_rows(__ballot_sync(0xffffffffu, lane < K && row >= 0 && cnt > 0));
   // ids >= N are never consumed: poison the row like the gather kernel does (last segment only)
-  if (lane < K && row >= 0 && blockIdx.y == gridDim.y - 1 && pos < len) p.P64[(int64_t)row * p.ldP] = NAN;
+  if (lane < K && row >= 0 && blockIdx.y == gridDim.y - 1 && pos < len) P64[(int64_t)row * p.ldP] = NAN;
   if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(p.flags, 1);
 }
 
 // ---- KL epilogue over the fp64 column sums -----------------------------------------------------
 template <int NACC>
 __global__ void __launch_bounds__(256)
-k_p64_epilogue(const double* __restrict__ P64, int64_t n_rows, int ldP, int G, const double* __restrict__ Q,
-               int n_perm, int64_t n_sel, const int* __restrict__ flags, double* __restrict__ out) {
+k_p64_epilogue(const double* __restrict__ P64, int n_seg, int64_t seg_stride, int64_t n_rows, int ldP, int G,
+               const double* __restrict__ Q, int n_perm, int64_t n_sel, const int* __restrict__ flags,
+               double* __restrict__ out) {
   if (*flags & 1) return;   // the fallback kernel produces the output
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -489,7 +486,10 @@ k_p64_epilogue(const double* __restrict__ P64, int64_t n_rows, int ldP, int G, c
 #pragma unroll
   for (int a = 0; a < NACC; ++a) {
     const int j = lane + 32 * a;
-    pr[a] = j < G ? P64[row * ldP + j] : 0.0;
+    double sum = 0.0;
+    if (j < G)
+      for (int sg = 0; sg < n_seg; ++sg) sum += P64[sg * seg_stride + row * ldP + j];   // fixed order
+    pr[a] = sum;
   }
   const double kl = hs_kl_epilogue<NACC>(pr, Q, G, lane);
   if (lane == 0) {
@@ -705,7 +705,6 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
                                             (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows, 0, 32, ctx->stream);
   const size_t keys_b = ((size_t)n_rows * 4 + 255) & ~(size_t)255;
   HS_TRY(hs_ensure(ctx, ctx->spmm_ws, 256 + 4 * keys_b + ((cub_bytes + 255) & ~(size_t)255)));
-  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_rows * ldP));
   char* w = (char*)ctx->spmm_ws.p;
   int* flags = (int*)w;                    w += 256;
   uint32_t* keys_in = (uint32_t*)w;        w += keys_b;
@@ -715,7 +714,6 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   void* cub_ws = w;
   cudaStream_t st = ctx->stream;
   HS_CUDA(ctx, cudaMemsetAsync(flags, 0, 256, st));
-  HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_rows * ldP, st));
   const int tb = 256;
   if (perm)
     k_row_len<true><<<(unsigned)((n_rows + tb - 1) / tb), tb, 0, st>>>(ptr_dev, n_rows, n_perm, keys_in, rows_in, flags);
@@ -743,12 +741,6 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
       HS_CUDA(ctx, cudaStreamSynchronize(st));
     }
     n_dense = ((int64_t)n_ge / 128) * 128;
-    if (n_dense > 0) {
-      const int rc = hs_run_csr_umma(ctx, rows_out, n_dense, ptr_dev, cols_dev, vals_dev, col_base,
-                                     (double*)ctx->part.p, ldP, flags);
-      if (rc == -1) n_dense = 0;
-      else if (rc != HS_OK) return rc;
-    }
   }
 
   // ---- the remaining rows: slab kernel ----
@@ -767,6 +759,16 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   if (n_tiles * 2 <= sms) n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms / n_tiles, total_slabs / 4));
   const int64_t seg_cells = ((total_slabs + n_seg - 1) / n_seg) * S;
   n_seg = (int)((ctx->N + seg_cells - 1) / seg_cells);
+  // fp64 column sums: one [n_rows][ldP] block per cell segment of either kernel (single writer per block
+  // and row; the epilogue adds the blocks in order, so repeated calls are bit-identical)
+  const int n_seg_umma = n_dense > 0 ? hs_csr_umma_segments(ctx, n_dense) : 0;
+  const int n_seg_all = hs_max(n_seg, hs_max(n_seg_umma, 1));
+  const int64_t seg_stride = n_rows * (int64_t)ldP;
+  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_seg_all * (size_t)seg_stride));
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_seg_all * (size_t)seg_stride, st));
+  if (n_dense > 0)
+    HS_TRY(hs_run_csr_umma(ctx, rows_out, n_dense, ptr_dev, cols_dev, vals_dev, col_base, (double*)ctx->part.p, ldP,
+                           seg_stride, n_seg_umma, flags));
   const size_t slots_b = ((size_t)n_slots * 8 + 255) & ~(size_t)255;
   const size_t slots4_b = ((size_t)n_slots * 4 + 255) & ~(size_t)255;
   HS_TRY(hs_ensure(ctx, ctx->spmm_slots, 2 * slots_b + 2 * slots4_b));
@@ -795,6 +797,7 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   prm.seg_cells = seg_cells;
   prm.n_seg = n_seg;
   prm.P64 = (double*)ctx->part.p;
+  prm.seg_stride = seg_stride;
   prm.ldP = ldP;
   prm.flags = flags;
 
@@ -813,7 +816,8 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   const double* Q = (const double*)ctx->Q.p;
   const int np = perm ? n_perm : out_n_perm;
   const int64_t nsel = perm ? n_units : out_n_sel;
-#define HS_EPI(NA) k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_rows, ldP, G, Q, np, nsel, flags, out_dev)
+#define HS_EPI(NA) \
+  k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_seg_all, seg_stride, n_rows, ldP, G, Q, np, nsel, flags, out_dev)
   if (nacc <= 1) HS_EPI(1);
   else if (nacc <= 2) HS_EPI(2);
   else if (nacc <= 3) HS_EPI(3);

@@ -195,7 +195,9 @@ struct UmmaParams {
   // split-K
   int64_t kblocks_per_seg;
   // output
-  double* P64;             // [n_rows][ldP], zeroed by the caller
+  double* P64;             // [segments][rows][ldP] fp64 sums, zeroed by the caller; one writer per
+                           // (segment, row, column), segments are added in order by the epilogue kernel
+  int64_t seg_stride;      // doubles between segments
   int ldP;
   int G;
   int* flags;              // bit 0: caller must rerun on the fallback kernel (fp16 overflow of an A value;
@@ -393,10 +395,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
         if (lane == 0) mbar_arrive(full_a(s));
       }
       cp_async_wait<0>();
-      // entries left after the last block of the last segment carry ids >= N: poison the row
+      // entries left after the last block of the last segment carry ids >= N: hand the call to the gather
+      // kernel, which poisons exactly those rows (an error path; speed is irrelevant)
       if (rowid >= 0 && blockIdx.y == gridDim.y - 1 && tail < end) {
         const int c = (int)lds_u32(ring_c + (uint32_t)((tail - pos0) & (kRing - 1)) * 512u) - p.col_base;
-        if (tail < head && c != 0x7fffffff) atomicAdd(p.P64 + (int64_t)rowid * p.ldP, (double)NAN);
+        if (tail < head && c != 0x7fffffff) violation = true;
       }
       if (__any_sync(0xffffffffu, violation || over) && lane == 0) atomicOr(p.flags, 1);
     } else
@@ -539,10 +542,10 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
     const double unscale = 1.0 / ((double)kScaleA * (double)kScaleD);
     auto flush = [&]() {
       if (row >= 0 && trow < p.n_rows) {
-        double* prow = p.P64 + row * p.ldP;
+        double* prow = p.P64 + blockIdx.y * p.seg_stride + row * p.ldP;
 #pragma unroll
         for (int c = 0; c < 64; ++c)
-          if (col0 + c < p.G) atomicAdd(prow + col0 + c, (double)acc2[c] * unscale);
+          if (col0 + c < p.G) prow[col0 + c] += (double)acc2[c] * unscale;
       }
 #pragma unroll
       for (int c = 0; c < 64; ++c) acc2[c] = 0.f;
@@ -583,8 +586,8 @@ constexpr size_t kUmmaSmemCsr = 1024 + (size_t)kStagesCsr * kStageBytes + 256 + 
 
 template <int NACC>
 __global__ void __launch_bounds__(256)
-k_p64_kl(const double* __restrict__ P64, int64_t n_rows, int ldP, int G, const double* __restrict__ Q,
-         const int* __restrict__ flags, double* __restrict__ out) {
+k_p64_kl(const double* __restrict__ P64, int n_seg, int64_t seg_stride, int64_t n_rows, int ldP, int G,
+         const double* __restrict__ Q, const int* __restrict__ flags, double* __restrict__ out) {
   if (*flags & 1) return;   // the SIMT rerun produces the output
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -593,7 +596,10 @@ k_p64_kl(const double* __restrict__ P64, int64_t n_rows, int ldP, int G, const d
 #pragma unroll
   for (int a = 0; a < NACC; ++a) {
     const int j = lane + 32 * a;
-    pr[a] = j < G ? P64[row * ldP + j] : 0.0;
+    double sum = 0.0;
+    if (j < G)
+      for (int sg = 0; sg < n_seg; ++sg) sum += P64[sg * seg_stride + row * ldP + j];   // fixed order
+    pr[a] = sum;
   }
   const double kl = hs_kl_epilogue<NACC>(pr, Q, G, lane);
   if (lane == 0) out[row] = kl;
@@ -625,11 +631,8 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   if (ctx->G > kTileN) return -1;
   HS_TRY(ensure_density_tiles(ctx));
   const int ldP = kTileN;
-  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_rows * ldP));
   HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
   cudaStream_t st = ctx->stream;
-  HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_rows * ldP, st));
-  HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
   const int row_tiles = (int)((n_rows + kTileM - 1) / kTileM);
   const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
   // split the cell axis until the grid covers the machine; segments are whole drain windows
@@ -637,6 +640,10 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   int64_t kb_per_seg = (total_kb + n_seg - 1) / n_seg;
   kb_per_seg = (kb_per_seg + kDrainBlocks - 1) / kDrainBlocks * kDrainBlocks;
   n_seg = (total_kb + kb_per_seg - 1) / kb_per_seg;
+  const int64_t seg_stride = n_rows * (int64_t)ldP;
+  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_seg * (size_t)seg_stride));
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_seg * (size_t)seg_stride, st));
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
   UmmaParams prm = {};
   prm.E = e_dev;
   prm.ld = ld;
@@ -649,6 +656,7 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
   prm.kblocks_per_seg = kb_per_seg;
   prm.P64 = (double*)ctx->part.p;
+  prm.seg_stride = seg_stride;
   prm.ldP = ldP;
   prm.G = ctx->G;
   prm.flags = (int*)ctx->umma_flags.p;
@@ -662,28 +670,41 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   }
   HS_LAUNCH_CHECK(ctx);
   const unsigned eb = (unsigned)((n_rows + 7) / 8);
-  k_p64_kl<4><<<eb, 256, 0, st>>>((const double*)ctx->part.p, n_rows, ldP, ctx->G, (const double*)ctx->Q.p,
+  k_p64_kl<4><<<eb, 256, 0, st>>>((const double*)ctx->part.p, (int)n_seg, seg_stride, n_rows, ldP, ctx->G, (const double*)ctx->Q.p,
                                   (const int*)ctx->umma_flags.p, out_dev);
   HS_LAUNCH_CHECK(ctx);
   if (flag_dev_out) *flag_dev_out = (const int*)ctx->umma_flags.p;
   return HS_OK;
 }
 
-// Tensor-core contraction of the n_dense densest CSR rows (tile row t = matrix row sorted_rows_dev[t]).
-// Adds into P64 (fp64 column sums, [rows][ldP], zeroed by the caller); flags bit 0 requests the fallback.
-// Returns -1 when the shape is not supported (G > 128).
-int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
-                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP, int* flags) {
-  if (n_dense <= 0) return HS_OK;
-  if (ctx->G > kTileN) return -1;
-  HS_TRY(ensure_density_tiles(ctx));
+// cell segments the CSR tensor-core launch uses: about two waves of CTAs, at least 64 blocks per segment
+static void csr_umma_plan(const hs_ctx* ctx, int64_t n_dense, int64_t* kb_per_seg, int64_t* n_seg) {
   const int row_tiles = (int)((n_dense + kTileM - 1) / kTileM);
   const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
-  // about two waves of CTAs; a segment is at least 64 blocks long
-  int64_t n_seg = hs_max<int64_t>(1, (2 * (int64_t)ctx->sm_count + row_tiles - 1) / row_tiles);
-  n_seg = hs_min<int64_t>(n_seg, hs_max<int64_t>(1, total_kb / 64));
-  const int64_t kb_per_seg = (total_kb + n_seg - 1) / n_seg;
-  n_seg = (total_kb + kb_per_seg - 1) / kb_per_seg;
+  int64_t ns = hs_max<int64_t>(1, (2 * (int64_t)ctx->sm_count + row_tiles - 1) / row_tiles);
+  ns = hs_min<int64_t>(ns, hs_max<int64_t>(1, total_kb / 64));
+  *kb_per_seg = (total_kb + ns - 1) / ns;
+  *n_seg = (total_kb + *kb_per_seg - 1) / *kb_per_seg;
+}
+
+int hs_csr_umma_segments(const hs_ctx* ctx, int64_t n_dense) {
+  int64_t kb = 0, ns = 0;
+  csr_umma_plan(ctx, n_dense, &kb, &ns);
+  return (int)ns;
+}
+
+// Tensor-core contraction of the n_dense densest CSR rows (tile row t = matrix row sorted_rows_dev[t]).
+// Adds into P64 ([n_seg][rows][ldP] fp64 column sums, zeroed by the caller); flags bit 0 requests the fallback.
+int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
+                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP,
+                    int64_t seg_stride, int n_seg_expected, int* flags) {
+  if (n_dense <= 0) return HS_OK;
+  if (ctx->G > kTileN) return hs_fail(ctx, HS_ERR_INVALID, "internal: tensor-core CSR path needs grid.points <= 128");
+  HS_TRY(ensure_density_tiles(ctx));
+  const int row_tiles = (int)((n_dense + kTileM - 1) / kTileM);
+  int64_t kb_per_seg = 0, n_seg = 0;
+  csr_umma_plan(ctx, n_dense, &kb_per_seg, &n_seg);
+  if (n_seg != n_seg_expected) return hs_fail(ctx, HS_ERR_INVALID, "internal: segment plan mismatch");
   UmmaParams prm = {};
   prm.sorted_rows = sorted_rows_dev;
   prm.ptr = ptr_dev;
@@ -696,6 +717,7 @@ int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense
   prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
   prm.kblocks_per_seg = kb_per_seg;
   prm.P64 = P64;
+  prm.seg_stride = seg_stride;
   prm.ldP = ldP;
   prm.G = ctx->G;
   prm.flags = flags;

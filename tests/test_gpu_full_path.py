@@ -159,3 +159,67 @@ def test_tensor_core_csr_rows_opt_in(ctx, monkeypatch):
     got = ctx.dkl_csr(p, j, v)
     assert _rel(base, want) < RTOL_DKL and _rel(got, want) < RTOL_DKL
     assert not np.array_equal(got, base)          # the densest rows really took the other path
+
+
+def test_front_door_dispatch_variants(ctx, toy, tmp_path):
+    """haystack(): data.frame coordinates, an AnnData-like object (the Seurat / SingleCellExperiment methods'
+    role, R/s3.R:46-87), `dims`, spline.method = "bs", dir.randomization output, weights.advanced.Q."""
+    import pandas as pd
+    import scipy.sparse as ssp
+    coord, expr = toy["coord"], toy["expression"]
+    names = list(toy["gene_names"])
+    common = dict(grid_coord=toy["grid60"], ctx=ctx, verbose=False, rng=7, gene_names=names)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        base = hh.haystack(coord, expr, **common)
+        # data.frame in, same numbers (to rounding: DataFrame.values is column-major, so scale() sums in
+        # another order) -- and the same call twice is bit-identical
+        df = pd.DataFrame(coord, columns=["tSNE1", "tSNE2"])
+        r_df = hh.haystack(df, expr, **common)
+        np.testing.assert_allclose(r_df["results"]["D_KL"].values, base["results"]["D_KL"].values, rtol=1e-12)
+        again = hh.haystack(coord, expr, **common)
+        np.testing.assert_array_equal(again["results"]["D_KL"].values, base["results"]["D_KL"].values)
+        np.testing.assert_array_equal(again["results"]["log.p.vals"].values, base["results"]["log.p.vals"].values)
+
+        class FakeAnnData:           # cells x genes, embedding in .obsm
+            X = ssp.csr_matrix(expr.T)
+            obsm = {"X_tsne": np.column_stack([coord, np.zeros(601)])}
+            layers = {}
+            var_names = pd.Index(names)
+        r_ad = hh.haystack(FakeAnnData(), coord="X_tsne", dims=[0, 1], grid_coord=toy["grid60"], ctx=ctx,
+                           verbose=False, rng=7)
+        assert list(r_ad["results"].index) == names
+        assert _rel(r_ad["results"]["D_KL"].values, base["results"]["D_KL"].values) < RTOL_DKL
+        with pytest.raises(ValueError, match="Please specify an embedding"):
+            hh.haystack(FakeAnnData())
+        # B-splines and the randomization dump
+        out = tmp_path / "rand"
+        r_bs = hh.haystack(coord, expr, spline_method="bs", dir_randomization=str(out), **common)
+        assert r_bs["info"]["randomization"]["method"] == "bs"
+        assert np.isfinite(r_bs["results"]["log.p.vals"].values).all()
+        dumped = np.loadtxt(out / "random.D_KL.csv", delimiter=",")
+        np.testing.assert_allclose(dumped, r_bs["info"]["randomization"]["KLD_rand"], rtol=1e-12)
+        # weights.advanced.Q changes Q (and therefore D_KL), never P (R/haystack_continuous.R:182)
+        w = 0.5 + (np.arange(601) % 5) / 2.0
+        r_w = hh.haystack(coord, expr, weights_advanced_Q=w, **common)
+    xs, _, _ = ho.scale_coords(coord)
+    dsw = ho.density_stage(xs, toy["grid60"], w)
+    want = ho.dkl_observed(expr, dsw["density"], dsw["Q"])
+    assert _rel(r_w["results"]["D_KL"].values, want) < RTOL_DKL
+    # strongly structured genes keep extreme p-values under either spline family
+    top_ns = set(hh.show_result_haystack(base, n=25).index)
+    top_bs = set(hh.show_result_haystack(r_bs, n=25).index)
+    assert len(top_ns & top_bs) >= 15
+
+
+def test_zero_variance_genes_are_filtered(ctx, toy):
+    """R/haystack_continuous.R:76-80: rows with sd == 0 are dropped before scoring."""
+    expr = toy["expression"].copy()
+    expr[3, :] = 0.0
+    expr[10, :] = 2.0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = hh.haystack(toy["coord"], expr, grid_coord=toy["grid60"], ctx=ctx, verbose=False, rng=1,
+                          gene_names=list(toy["gene_names"]))
+    assert res["results"].shape == (498, 3)
+    assert "gene_4" not in res["results"].index and "gene_11" not in res["results"].index

@@ -55,9 +55,9 @@ def test_csr_invariances_and_spot_parity(ctx, big):
         j2[p[g]:p[g + 1]] = j[perm]
         v2[p[g]:p[g + 1]] = v[perm]
     assert _rel(ctx.dkl_csr(p, j2, v2), base) < 2e-6
-    # int32 and int64 row pointers are the same call (with few rows the cell axis is split over CTAs and the
-    # fp64 partial sums meet in atomics, so repeated calls agree to rounding, not bit for bit)
-    np.testing.assert_allclose(ctx.dkl_csr(p.astype(np.int32), j, v), base, rtol=1e-12)
+    # int32 and int64 row pointers are the same call, bit for bit (the per-segment fp64 sums are added in a
+    # fixed order)
+    np.testing.assert_array_equal(ctx.dkl_csr(p.astype(np.int32), j, v), base)
     # a few genes against the fp64 oracle (density recomputed on the host for those cells only)
     from scipy.spatial.distance import cdist
     bw, q = big["dens"]["bandwidth"], big["dens"]["Q"]
