@@ -561,7 +561,7 @@ __device__ __forceinline__ int div_magic(uint32_t id, uint64_t magic) { return (
 
 constexpr int kSortUnroll = 8;   // independent loads in flight per thread
 constexpr int kSortMaxParts = 8;      // output-range parts per row (grid.y)
-constexpr int kSortPartItems = 32768; // target entries per part: 256 KB of pairs, so that the scatter
+constexpr int kSortPartItemsDefault = 262144; // target entries per part (measured best of 16k..2M at C5): 256 KB of pairs, so that the scatter
                                       // windows of all resident CTAs stay in L2 until their sectors fill
 
 // Writes (id, value) pairs in slab order.  A row is split into up to kSortMaxParts contiguous bin ranges,
@@ -571,7 +571,7 @@ constexpr int kSortPartItems = 32768; // target entries per part: 256 KB of pair
 __global__ void __launch_bounds__(kSortThreads, 2)
 k_perm_slab_sort(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
                  const float* __restrict__ vals, const int32_t* __restrict__ ind, int index_base, int64_t N,
-                 uint64_t magic, int n_bins, uint2* __restrict__ pairs_out) {
+                 uint64_t magic, int n_bins, int kSortPartItems, uint2* __restrict__ pairs_out) {
   extern __shared__ unsigned int hist[];      // [bins of this part + 1]
   __shared__ unsigned int warp_tot[kSortThreads / 32];
   __shared__ unsigned int before_tot;
@@ -854,8 +854,10 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
   HS_CUDA(ctx, cudaFuncSetAttribute(k_perm_slab_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const uint64_t magic = ((1ull << 40) + (uint64_t)S - 1) / (uint64_t)S;
   if (n_rows * kSortMaxParts > 0x7fffffffLL) return -1;
+  int part_items = kSortPartItemsDefault;
+  if (const char* e = getenv("HS_SORT_PART_ITEMS")) part_items = hs_max(1024, atoi(e));
   k_perm_slab_sort<<<(unsigned)(n_rows * kSortMaxParts), kSortThreads, smem, st>>>(
-      rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base, ctx->N, magic, n_bins, (uint2*)ctx->perm_cols.p);
+      rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base, ctx->N, magic, n_bins, part_items, (uint2*)ctx->perm_cols.p);
   HS_LAUNCH_CHECK(ctx);
   return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
                           /*allow_umma=*/false /* ids are only slab-sorted */, nullptr, ctx->perm_cols.p);
