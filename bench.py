@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-genes", type=int, default=0, help="0 = all genes if host memory allows")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-f32", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the side measurement of the dense (tcgen05) kernel")
     ap.add_argument("--dense-genes", type=int, default=1024)
@@ -481,9 +482,13 @@ def run_b200(a):
         dense_extra = run_dense_side(a, ctx, dev, peak)
 
     # ---- end to end through the host-pointer C ABI (pinned host inputs, H2D inside the timed region) ----
-    e2e = None
+    e2e = e2e32 = None
     if not a.no_e2e:
         e2e = run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_local, world, rank, dev)
+        if world == 1 and not a.no_e2e_f32:
+            # the same through the float32 entry points (hosts that hold float32 matrices, e.g. AnnData)
+            e2e32 = run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_local, world, rank, dev,
+                            value_dtype="float32")
 
     # ---- CPU baseline + parity spot check (rank 0, N = 1 only) ----
     cpu = None
@@ -509,7 +514,9 @@ def run_b200(a):
         if e2e is not None:
             line["e2e"] = e2e
         if dense_extra is not None:
-            line["extra"] = {"k2_dense_tcgen05": dense_extra}
+            line.setdefault("extra", {})["k2_dense_tcgen05"] = dense_extra
+        if e2e32 is not None:
+            line.setdefault("extra", {})["e2e_float32_host"] = e2e32
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if parity is not None:
@@ -562,7 +569,8 @@ def _ncu_traffic():
     return None
 
 
-def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_local, world, rank, dev):
+def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_local, world, rank, dev,
+            value_dtype="float64"):
     import psutil
     import torch
     import torch.distributed as dist
@@ -578,13 +586,15 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     p_h = p[:m_e2e + 1].cpu()
     nnz_e = int(p_h[-1])
     # R hands over doubles (dgRMatrix@x); keep them in pinned memory as the contract asks
+    vdt = torch.float64 if value_dtype == "float64" else torch.float32
+    vbytes = 8.0 if value_dtype == "float64" else 4.0
     j_h = torch.empty(nnz_e, dtype=torch.int32).pin_memory()
     j_h.copy_(cols[:nnz_e])
-    x_h = torch.empty(nnz_e, dtype=torch.float64).pin_memory()
-    x_h.copy_(vals[:nnz_e].double())
+    x_h = torch.empty(nnz_e, dtype=vdt).pin_memory()
+    x_h.copy_(vals[:nnz_e].to(vdt))
     gp_h = gene_ptr.cpu().numpy()
-    pv_h = torch.empty(int(pval.numel()), dtype=torch.float64).pin_memory()
-    pv_h.copy_(pval.double())
+    pv_h = torch.empty(int(pval.numel()), dtype=vdt).pin_memory()
+    pv_h.copy_(pval.to(vdt))
     pi_h = torch.empty(n_ind, dtype=torch.int32).pin_memory()
     pi_h.copy_(pind)
     xs_h = torch.from_numpy(np.ascontiguousarray(xs.T)).pin_memory()       # column-major N x d
@@ -618,12 +628,12 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     per = dt / a.e2e_steps
-    h2d = (8.0 * a.cells * a.dims + 8.0 * a.grid_points * a.dims + 8.0 * (m_e2e + 1) + 12.0 * nnz_e
-           + 8.0 * len(gp_h) + 8.0 * int(pval.numel()) + 4.0 * n_ind)
+    h2d = (8.0 * a.cells * a.dims + 8.0 * a.grid_points * a.dims + 8.0 * (m_e2e + 1) + (4.0 + vbytes) * nnz_e
+           + 8.0 * len(gp_h) + vbytes * int(pval.numel()) + 4.0 * n_ind)
     d2h = 8.0 * m_e2e + 8.0 * n_sel_local * r_loc + 8.0 * a.grid_points + 8.0
     return {"value": m_e2e * world / per, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": per * 1e3, "steps": a.e2e_steps, "genes_per_gpu": m_e2e,
-            "note": ("hs_density + hs_dkl_csr + hs_dkl_perm_csr with pinned host buffers (fp64 values, int32 ids), "
+            "note": (f"hs_density + hs_dkl_csr + hs_dkl_perm_csr with pinned host buffers ({value_dtype} values, int32 ids), "
                      "timed with the host clock around the blocking calls"
                      + ("" if m_e2e == m else f"; host memory limits the e2e pass to the first {m_e2e} genes"))}
 

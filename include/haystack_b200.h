@@ -99,6 +99,12 @@ int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, d
 int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x,
                int64_t n_genes, double* dkl_out);
 
+/* The same with single-precision values, for hosts that hold float32 matrices (AnnData / scanpy default):
+ * the kernels multiply in fp32 either way, so nothing is lost and a third of the upload is saved.
+ * (R has no single-precision vectors; the R shim uses hs_dkl_csr.) */
+int hs_dkl_csr_f32(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const float* x,
+                   int64_t n_genes, double* dkl_out);
+
 /* ---- randomized D_KL (K4) --------------------------------------------------------------- */
 /* Dense form: v[n_cells] is the gene's expression row; perm is n_cells x n_perm column-major,
  * column r being sample.int(n_cells) (values index_base .. n_cells-1+index_base; R passes
@@ -113,6 +119,9 @@ int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_p
  * in order with val (:275).  out is n_sel x n_perm column-major (all.D_KL.randomized, :245). */
 int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val,
                     const int32_t* ind, int n_perm, int index_base, double* out);
+
+int hs_dkl_perm_csr_f32(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const float* val,
+                        const int32_t* ind, int n_perm, int index_base, double* out);
 
 /* ---- device-resident variants (inputs already in HBM; used by bench.py and by the
  *      multi-GPU host layer).  Pointers are device pointers in this process. --------------- */

@@ -324,8 +324,11 @@ int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
 // launch over all rows -- the contraction kernels need many rows per launch to fill the machine.
 // If the batch does not fit into free device memory the units are processed in several batches.
 //   hp[u]  : prefix offsets in values per unit (row or selected gene); ids per unit = values * ipv
-static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const int32_t* ids, const double* vals,
-                          int64_t ipv, bool perm, int n_perm, int index_base, double* dev_out, int timer_slot) {
+static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const int32_t* ids, const void* vals_any,
+                          bool vals_f32, int64_t ipv, bool perm, int n_perm, int index_base, double* dev_out,
+                          int timer_slot) {
+  const double* vals = (const double*)vals_any;       // when !vals_f32
+  const float* vals32h = (const float*)vals_any;      // when vals_f32: straight into place, no conversion
   const int64_t v0 = hp[0], n_vals = hp[n_units] - v0, n_ids = n_vals * ipv;
   const size_t chunk = env_size("HS_STAGE_VALUES", (size_t)16 << 20);   // values per staging buffer
   HS_TRY(hs_ensure(ctx, ctx->ptrs, sizeof(int64_t) * (size_t)(n_units + 1)));
@@ -370,8 +373,13 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
     const int64_t a0 = rel[u0], a1 = rel[u1];
     for (int64_t off = a0; off < a1; off += (int64_t)stage_vals) {
       const int64_t n = hs_min<int64_t>((int64_t)stage_vals, a1 - off);
-      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
-      HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p + off, n, cs));
+      if (vals_f32) {
+        HS_CUDA(ctx, cudaMemcpyAsync((float*)ctx->vals32.p + off, vals32h + v0 + off, sizeof(float) * (size_t)n,
+                                     cudaMemcpyHostToDevice, cs));
+      } else {
+        HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
+        HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p + off, n, cs));
+      }
     }
     // ids: straight into place, in pieces so that pageable sources do not serialise one huge copy
     for (int64_t off = a0 * ipv; off < a1 * ipv; off += id_piece) {
@@ -396,7 +404,7 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
 // Split the units into batches that fit into device memory and run them one after the other.
 // Each batch b covers units [ub, ue) and writes `out_per_unit` doubles per unit: contiguous for CSR rows;
 // for the permutation form a batch-local (ue-ub) x n_perm column-major block that is re-laid out on the host.
-static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_t* ids, const double* vals,
+static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_t* ids, const void* vals, bool vals_f32,
                        int64_t ipv, bool perm, int n_perm, int index_base, double* host_out, int timer_slot) {
   const int64_t n_units = (int64_t)hp.size() - 1;
   const int64_t per_unit = perm ? n_perm : 1;
@@ -415,7 +423,7 @@ static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_
     int64_t ue = ub + 1;
     while (ue < n_units && (double)(hp[ue + 1] - hp[ub]) * bytes_per_value <= budget) ++ue;
     double* dev_out = (double*)ctx->out.p + ub * per_unit;
-    HS_TRY(upload_and_run(ctx, hp.data() + ub, ue - ub, ids, vals, ipv, perm, n_perm, index_base,
+    HS_TRY(upload_and_run(ctx, hp.data() + ub, ue - ub, ids, vals, vals_f32, ipv, perm, n_perm, index_base,
                           dev_out, timer_slot));
     if (!perm || (ub == 0 && ue == n_units)) {
       HS_CUDA(ctx, cudaMemcpyAsync(host_out + ub * per_unit, dev_out, sizeof(double) * (size_t)((ue - ub) * per_unit),
@@ -434,8 +442,8 @@ static int staged_rows(hs_ctx* ctx, const std::vector<int64_t>& hp, const int32_
   return HS_OK;
 }
 
-int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
-               double* dkl_out) {
+static int dkl_csr_any(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const void* x, bool x_f32,
+                       int64_t n_genes, double* dkl_out) {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || !p || !dkl_out) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: bad arguments");
@@ -447,11 +455,21 @@ int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const 
     if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: row pointers must be non-decreasing");
   if (hp[n_genes] > hp[0] && (!j || !x)) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr: j/x are NULL");
   // j and x are the caller's whole slots; rows start at element hp[0]
-  return staged_rows(ctx, hp, j, x, 1, false, 1, 0, dkl_out, HS_T_CSR);
+  return staged_rows(ctx, hp, j, x, x_f32, 1, false, 1, 0, dkl_out, HS_T_CSR);
 }
 
-int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, const int32_t* ind,
-                    int n_perm, int index_base, double* out) {
+int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
+               double* dkl_out) {
+  return dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out);
+}
+
+int hs_dkl_csr_f32(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const float* x, int64_t n_genes,
+                   double* dkl_out) {
+  return dkl_csr_any(ctx, p, p_is_64, j, x, true, n_genes, dkl_out);
+}
+
+static int dkl_perm_csr_any(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const void* val, bool val_f32,
+                            const int32_t* ind, int n_perm, int index_base, double* out) {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_sel < 0 || n_perm <= 0 || !gene_ptr || !out)
@@ -462,7 +480,17 @@ int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const d
   for (int64_t i = 0; i < n_sel; ++i)
     if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: gene_ptr must be non-decreasing");
   if (hp[n_sel] > 0 && (!val || !ind)) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr: val/ind are NULL");
-  return staged_rows(ctx, hp, ind, val, n_perm, true, n_perm, index_base, out, HS_T_PERM);
+  return staged_rows(ctx, hp, ind, val, val_f32, n_perm, true, n_perm, index_base, out, HS_T_PERM);
+}
+
+int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, const int32_t* ind,
+                    int n_perm, int index_base, double* out) {
+  return dkl_perm_csr_any(ctx, gene_ptr, n_sel, val, false, ind, n_perm, index_base, out);
+}
+
+int hs_dkl_perm_csr_f32(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const float* val, const int32_t* ind,
+                        int n_perm, int index_base, double* out) {
+  return dkl_perm_csr_any(ctx, gene_ptr, n_sel, val, true, ind, n_perm, index_base, out);
 }
 
 int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* dkl_out) {

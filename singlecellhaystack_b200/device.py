@@ -203,9 +203,15 @@ class DeviceContext:
             p = np.ascontiguousarray(p, dtype=np.int32)
             is64 = 0
         j = np.ascontiguousarray(j, dtype=np.int32)
-        x = np.ascontiguousarray(x, dtype=np.float64)
+        x = np.asarray(x)
         m = p.size - 1
         out = np.empty(max(m, 0), dtype=np.float64)
+        if x.dtype == np.float32:      # float32 hosts (AnnData): no widening, a third less to upload
+            x = np.ascontiguousarray(x)
+            self._check(self._lib.hs_dkl_csr_f32(self._h, _ptr(p), is64, _ptr(j), _ptr(x), m, _ptr(out)),
+                        "hs_dkl_csr_f32")
+            return out
+        x = np.ascontiguousarray(x, dtype=np.float64)
         self._check(self._lib.hs_dkl_csr(self._h, _ptr(p), is64, _ptr(j), _ptr(x), m, _ptr(out)), "hs_dkl_csr")
         return out
 
@@ -246,13 +252,16 @@ class DeviceContext:
         """hs_dkl_perm_csr on already flattened host arrays (gene_ptr int64 [S+1], val fp64, ind int32
         laid out gene by gene as nnz_s x n_perm column-major blocks).  No host-side copies."""
         gene_ptr = np.ascontiguousarray(gene_ptr, dtype=np.int64)
-        val = np.ascontiguousarray(val, dtype=np.float64)
+        val = np.asarray(val)
+        f32 = val.dtype == np.float32
+        val = np.ascontiguousarray(val, dtype=np.float32 if f32 else np.float64)
         ind = np.ascontiguousarray(ind, dtype=np.int32)
         s_ = gene_ptr.size - 1
         if out is None:
             out = np.empty((s_, int(n_perm)), dtype=np.float64, order="F")
-        self._check(self._lib.hs_dkl_perm_csr(self._h, _ptr(gene_ptr), s_, _ptr(val), _ptr(ind), int(n_perm),
-                                              int(index_base), _ptr(out)), "hs_dkl_perm_csr")
+        fn = self._lib.hs_dkl_perm_csr_f32 if f32 else self._lib.hs_dkl_perm_csr
+        self._check(fn(self._h, _ptr(gene_ptr), s_, _ptr(val), _ptr(ind), int(n_perm), int(index_base), _ptr(out)),
+                    "hs_dkl_perm_csr")
         return out
 
     # -- device-resident variants -------------------------------------------------------------

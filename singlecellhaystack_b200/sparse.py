@@ -28,7 +28,9 @@ class dgRMatrix:
     def __post_init__(self):
         self.p = np.ascontiguousarray(self.p, dtype=np.int64 if np.asarray(self.p).dtype == np.int64 else np.int32)
         self.j = np.ascontiguousarray(self.j, dtype=np.int32)
-        self.x = np.ascontiguousarray(self.x, dtype=np.float64)
+        # R's @x is double; float32 hosts (AnnData) keep their width -- the device multiplies in fp32 anyway
+        xa = np.asarray(self.x)
+        self.x = np.ascontiguousarray(xa, dtype=np.float32 if xa.dtype == np.float32 else np.float64)
         self.Dim = (int(self.Dim[0]), int(self.Dim[1]))
         if self.p.size != self.Dim[0] + 1:
             raise ValueError("slot p must have nrow+1 entries")

@@ -89,6 +89,8 @@ def test_synthetic_csr_parity(ctx, n, d, g, m, rho):
     want = ho.dkl_observed(ho.RowSparse(p=p, j=j, x=v, shape=(m, n)), ref["density"], ref["Q"])
     got = ctx.dkl_csr(p, j, v)
     assert _rel(got, want) < RTOL_DKL
+    # float32 host values (hs_dkl_csr_f32): the device rounds doubles to fp32 the same way -> identical bits
+    np.testing.assert_array_equal(ctx.dkl_csr(p, j, v.astype(np.float32)), got)
     # dense form of the same rows
     dense = ho.RowSparse(p=p, j=j, x=v, shape=(m, n)).to_dense()
     got_d = ctx.dkl_dense(dense[:32])
@@ -103,7 +105,12 @@ def test_synthetic_csr_parity(ctx, n, d, g, m, rho):
         ids_o.append(ids)
         ids_d.append(np.asfortranarray(ids.T))
     want_r = ho.dkl_randomized_sparse(vals, ids_o, ref["density"], ref["Q"])
-    assert _rel(ctx.dkl_perm_csr(vals, ids_d, index_base=1), want_r) < RTOL_DKL
+    got_r = ctx.dkl_perm_csr(vals, ids_d, index_base=1)
+    assert _rel(got_r, want_r) < RTOL_DKL
+    gp = np.concatenate([[0], np.cumsum([len(a_) for a_ in vals])]).astype(np.int64)
+    flat32 = ctx.dkl_perm_csr_flat(gp, np.concatenate(vals).astype(np.float32),
+                                   np.concatenate([a_.ravel(order="F") for a_ in ids_d]), 10, index_base=1)
+    assert _rel(flat32, want_r) < RTOL_DKL
 
 
 def test_sharded_layer_on_device(ctx, toy):
