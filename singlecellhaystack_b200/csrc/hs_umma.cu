@@ -24,6 +24,8 @@
 // 4 streams the B tiles, 5 owns TMEM and issues the MMAs, 8-15 drain TMEM and accumulate.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "hs_common.cuh"
 
@@ -40,7 +42,7 @@ constexpr int kStageBytes = 4 * kTileBytes;           // A_hi, A_lo, B_hi, B_lo
 constexpr int kDrainBlocks = 1;      // TMEM -> registers after every stage (64 cells = 4 accumulating MMAs per sum)
 constexpr int kFlushDrains = 16;     // registers -> fp64 every 16 drains (1024 cells)
 constexpr int kUmmaThreads = 512;
-constexpr float kScaleA = 0.125f;            // 2^-3
+constexpr float kScaleA = 1.0f;              // expression values go in unscaled (fp16 overflow -> fp32 kernel)
 constexpr float kScaleD = 16384.f;           // 2^14
 constexpr float kLoScale = 2048.f;           // 2^11
 constexpr uint32_t kLbo = 1024, kSbo = 2048;
@@ -112,6 +114,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 16 consecutive fp32 columns of this thread's TMEM lane (no wait: the caller batches loads)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // shared-memory matrix descriptor: MN-major, 128B swizzle, LBO / SBO as above, sm_100 version bit
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(kLbo >> 4) << 16) | ((uint64_t)(kSbo >> 4) << 32) |
@@ -127,23 +141,25 @@ __device__ __host__ __forceinline__ uint32_t chunk_off(int mg, int k) {
   return (uint32_t)(((kg * 2 + mi) << 10) + (k8 << 7) + ((c8 ^ k8) << 4));
 }
 
-// split 8 scaled floats into fp16 hi / lo (lo pre-multiplied by 2^11) and pack each as one 16-byte chunk
+// split 8 scaled floats into fp16 hi / lo (lo pre-multiplied by 2^11) and pack each as one 16-byte chunk.
+// Returns true when a finite value does not fit fp16 (|x| > 65504; Inf inputs take the same exit and are
+// then handled by the fp32 kernel exactly like the reference's arithmetic would).
 __device__ __forceinline__ bool split8(const float (&x)[8], uint4& hi, uint4& lo) {
   __half2 h[4], l[4];
-  bool over = false;
+  float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float a = x[2 * i], b = x[2 * i + 1];
+    amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(b)));
     h[i] = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h[i]);
-    over |= (isinf(hf.x) && !isinf(a)) || (isinf(hf.y) && !isinf(b));
     l[i] = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
   }
   hi = make_uint4(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]),
                   *reinterpret_cast<uint32_t*>(&h[2]), *reinterpret_cast<uint32_t*>(&h[3]));
   lo = make_uint4(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]),
                   *reinterpret_cast<uint32_t*>(&l[2]), *reinterpret_cast<uint32_t*>(&l[3]));
-  return over;
+  return amax > 65504.f;
 }
 __device__ __forceinline__ void sts_u4(uint32_t a, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -200,11 +216,20 @@ struct UmmaParams {
   int64_t seg_stride;      // doubles between segments
   int ldP;
   int G;
+  long long* dbg;          // optional (HS_UMMA_DEBUG): per-role wait cycles of CTA (0,0), 16 slots
   int* flags;              // bit 0: caller must rerun on the fallback kernel (fp16 overflow of an A value;
                            //        csr: column ids not ascending)
 };
 
-enum { kModeDense = 0, kModePerm = 1, kModeCsr = 2 };
+enum { kModeDense = 0, kModePerm = 1, kModeCsr = 2, kModeDenseTma = 3 };
+constexpr int kRawSlots = 3;                       // dense-tma: ring of raw fp32 tiles (64 cells x 128 rows)
+constexpr int kRawBytes = kBK * kTileM * 4;        // 32 KB
+
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+  return r;
+}
 
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
@@ -224,9 +249,11 @@ __device__ __forceinline__ void sts_u16(uint32_t a, unsigned short v) {
 template <int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams p) {
   constexpr bool PERM = MODE == kModePerm;
-  constexpr int kStages = MODE == kModeCsr ? kStagesCsr : kStagesDense;
-  // dense mode uses the two otherwise idle warps (6, 7) as extra producers
-  constexpr int kProducerWarps = MODE == kModeDense ? 6 : 4;
+  constexpr bool TMA = MODE == kModeDenseTma;
+  constexpr int kStages = (MODE == kModeCsr || TMA) ? 2 : kStagesDense;
+  // dense mode uses the two otherwise idle warps (6, 7) as extra producers; dense-tma uses warp 6 as a
+  // producer and warp 7 to stream raw fp32 tiles of E into a shared-memory ring with cp.async.bulk
+  constexpr int kProducerWarps = MODE == kModeDense ? 6 : (TMA ? 5 : 4);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // 1024-byte aligned operand stages (swizzle atoms), then barriers
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -240,8 +267,24 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   auto empty = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tmem_full = [&](int b) { return bar_base + 8u * (3 * kStages + b); };
   auto tmem_empty = [&](int b) { return bar_base + 8u * (3 * kStages + 2 + b); };
+  auto raw_full = [&](int r) { return bar_base + 8u * (3 * kStages + 4 + r); };                 // dense-tma only
+  auto raw_empty = [&](int r) { return bar_base + 8u * (3 * kStages + 4 + kRawSlots + r); };
+  const uint32_t raw_base = ring_base;   // same region as the csr rings: after stages + barriers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // development aid: cycles each role spends blocked on each barrier (CTA (0,0) only)
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  long long w_acc[3] = {0, 0, 0};
+  auto timed_wait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (dbg_on) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      w_acc[slot] += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  const long long t_begin = clock64();
   const int64_t row0 = (int64_t)blockIdx.x * kTileM;
   const int64_t total_kb = (p.N + kBK - 1) / kBK;
   const int64_t kb_begin = (int64_t)blockIdx.y * p.kblocks_per_seg;
@@ -259,6 +302,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
       mbar_init(tmem_full(b), 1);
       mbar_init(tmem_empty(b), 8);
     }
+    if (TMA)
+      for (int r = 0; r < kRawSlots; ++r) {
+        mbar_init(raw_full(r), 1);
+        mbar_init(raw_empty(r), kProducerWarps);
+      }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -267,7 +315,25 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4 || (MODE == kModeDense && (warp == 6 || warp == 7))) {
+  if (TMA && warp == 7) {
+    // ================= raw E tiles: one 512-byte bulk copy per cell, three stages ahead =================
+    {
+      // all 32 lanes issue copies (two cells each): a single thread cannot issue 64 small bulk copies per
+      // stage fast enough
+      const uint32_t row_bytes = (uint32_t)hs_min<int64_t>(kTileM, p.n_rows - row0) * 4u;
+      for (int i = 0; i < n_kb; ++i) {
+        const int r = i % kRawSlots;
+        if (i >= kRawSlots) timed_wait(raw_empty(r), ((i / kRawSlots) - 1) & 1, 0);
+        const int64_t c0 = (kb_begin + i) * kBK;
+        const int ncell = (int)hs_min<int64_t>(kBK, p.N - c0);
+        if (lane == 0) mbar_arrive_expect_tx(raw_full(r), (uint32_t)ncell * row_bytes);
+        __syncwarp();
+        const uint32_t dst = raw_base + (uint32_t)r * kRawBytes;
+        for (int k = lane; k < ncell; k += 32)
+          bulk_g2s(dst + (uint32_t)k * (kTileM * 4), p.E + row0 + (c0 + k) * p.ld, row_bytes, raw_full(r));
+      }
+    }
+  } else if (warp < 4 || (MODE == kModeDense && (warp == 6 || warp == 7)) || (TMA && warp == 6)) {
     // ================= A producers =================
     bool over = false;
     if (MODE == kModeCsr) {
@@ -405,10 +471,43 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
     } else
     for (int i = 0; i < n_kb; ++i) {
       const int s = i % kStages;
-      if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
+      if (i >= kStages) timed_wait(empty(s), ((i / kStages) - 1) & 1, 0);
       const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kTileBytes;
       const int64_t c0 = (kb_begin + i) * kBK;
-      if (!PERM) {
+      if (TMA) {
+        // the raw tile of this stage sits in shared memory (warp 7 requested it three stages ago): read,
+        // split, write the swizzled operand chunks.  160 producer threads, 6-7 tasks each.
+        const int pt = (warp < 4 ? warp : 4) * 32 + lane;                    // 0..159
+        const int r = i % kRawSlots;
+        timed_wait(raw_full(r), (i / kRawSlots) & 1, 1);
+        const uint32_t raw = raw_base + (uint32_t)r * kRawBytes;
+        const bool full_tile = (c0 + kBK <= p.N) && (row0 + kTileM <= p.n_rows);   // no stale bytes to mask
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const int t = pt + 160 * q;
+          if (t < 1024) {
+            const int mg = t & 15, k = t >> 4;
+            const float4 u = lds_f4(raw + (uint32_t)t * 32u);            // == k * 512 + mg * 32
+            const float4 w = lds_f4(raw + (uint32_t)t * 32u + 16u);
+            float x[8] = {u.x, u.y, u.z, u.w, w.x, w.y, w.z, w.w};
+            if (!full_tile) {
+              const bool cell_ok = c0 + k < p.N;
+              const int64_t rr = row0 + 8 * mg;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = (cell_ok && rr + e < p.n_rows) ? x[e] : 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] *= kScaleA;
+            uint4 hi, lo;
+            over |= split8(x, hi, lo);
+            const uint32_t off = chunk_off(mg, k);
+            sts_u4(a_hi + off, hi);
+            sts_u4(a_lo + off, lo);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(raw_empty(r));
+      } else if (!PERM) {
         // task = (row group of 8, cell): lanes 0-15 cover 128 rows of one cell, 16-31 the next cell.
         // 192 producer threads, 5-6 tasks each.  All of a stage's loads are issued before the first
         // conversion (one memory round trip per stage instead of one per task), and the lines the stage
@@ -488,15 +587,18 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
     if (__any_sync(0xffffffffu, over) && lane == 0) atomicOr(p.flags, 1);
   } else if (warp == 4) {
     // ================= B loader =================
-    if (lane == 0) {
+    {
       for (int i = 0; i < n_kb; ++i) {
         const int s = i % kStages;
-        if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
-        const uint32_t b_hi = smem_base + s * kStageBytes + 2 * kTileBytes;
-        const size_t off = (size_t)(kb_begin + i) * kTileBytes;
-        mbar_arrive_expect_tx(full_b(s), 2 * kTileBytes);
-        bulk_g2s(b_hi, p.Dh + off, kTileBytes, full_b(s));
-        bulk_g2s(b_hi + kTileBytes, p.Dl + off, kTileBytes, full_b(s));
+        if (i >= kStages) timed_wait(empty(s), ((i / kStages) - 1) & 1, 0);   // (L2 prefetching the tiles six stages ahead was tried: slower)
+        if (lane == 0) {
+          const uint32_t b_hi = smem_base + s * kStageBytes + 2 * kTileBytes;
+          const size_t off = (size_t)(kb_begin + i) * kTileBytes;
+          mbar_arrive_expect_tx(full_b(s), 2 * kTileBytes);
+          bulk_g2s(b_hi, p.Dh + off, kTileBytes, full_b(s));
+          bulk_g2s(b_hi + kTileBytes, p.Dl + off, kTileBytes, full_b(s));
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 5) {
@@ -507,11 +609,11 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
         const int d = i / kDrainBlocks, buf = d & 1;
         const bool first = (i % kDrainBlocks) == 0;
         if (first && d >= 2) {
-          mbar_wait(tmem_empty(buf), ((d >> 1) - 1) & 1);
+          timed_wait(tmem_empty(buf), ((d >> 1) - 1) & 1, 2);
           tc_fence_after();
         }
-        mbar_wait(full_a(s), (i / kStages) & 1);
-        mbar_wait(full_b(s), (i / kStages) & 1);
+        timed_wait(full_a(s), (i / kStages) & 1, 0);
+        timed_wait(full_b(s), (i / kStages) & 1, 1);
         tc_fence_after();
         const uint32_t st = smem_base + s * kStageBytes;
         const uint32_t acc0 = tmem_base + (uint32_t)(buf * 256), acc1 = acc0 + 128;
@@ -545,25 +647,25 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
         double* prow = p.P64 + blockIdx.y * p.seg_stride + row * p.ldP;
 #pragma unroll
         for (int c = 0; c < 64; ++c)
-          if (col0 + c < p.G) prow[col0 + c] += (double)acc2[c] * unscale;
+          if (col0 + c < p.G) atomicAdd(prow + col0 + c, (double)acc2[c] * unscale);   // single writer: order fixed
       }
 #pragma unroll
       for (int c = 0; c < 64; ++c) acc2[c] = 0.f;
     };
     for (int d = 0; d < n_drains; ++d) {
       const int buf = d & 1;
-      mbar_wait(tmem_full(buf), (d >> 1) & 1);
+      timed_wait(tmem_full(buf), (d >> 1) & 1, 0);
       tc_fence_after();
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        float a[32];
-        tmem_ld32(lane_addr + (uint32_t)(buf * 256 + 128 + col0 + 32 * h), a);       // cross terms, scale 2^-11
+      for (int h = 0; h < 4; ++h) {
+        if (col0 + 16 * h >= p.G) continue;                  // columns past the grid are zero padding
+        uint32_t a[16], m[16];                               // both loads in flight, one wait
+        tmem_ld16_nowait(lane_addr + (uint32_t)(buf * 256 + 128 + col0 + 16 * h), a);   // cross terms, scale 2^-11
+        tmem_ld16_nowait(lane_addr + (uint32_t)(buf * 256 + col0 + 16 * h), m);         // hi * hi
+        tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) a[c] *= (1.0f / kLoScale);
-        float m[32];
-        tmem_ld32(lane_addr + (uint32_t)(buf * 256 + col0 + 32 * h), m);             // hi * hi
-#pragma unroll
-        for (int c = 0; c < 32; ++c) acc2[32 * h + c] += m[c] + a[c];
+        for (int c = 0; c < 16; ++c)
+          acc2[16 * h + c] += fmaf(__uint_as_float(a[c]), 1.0f / kLoScale, __uint_as_float(m[c]));
       }
       tc_fence_before();
       __syncwarp();
@@ -571,6 +673,16 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
       if ((d % kFlushDrains) == kFlushDrains - 1) flush();
     }
     flush();
+  }
+  if (dbg_on && lane == 0) {
+    // slots: [0] total cycles; producer warp 0: [1] empty/raw_empty, [2] raw_full; raw loader (warp 7): [3];
+    // B loader: [4]; MMA: [5] full_a, [6] full_b, [7] tmem_empty; epilogue warp 8: [8] tmem_full
+    if (warp == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w_acc[0]; p.dbg[2] = w_acc[1]; }
+    if (warp == 7) p.dbg[3] = w_acc[0];
+    if (warp == 4) p.dbg[4] = w_acc[0];
+    if (warp == 5) { p.dbg[5] = w_acc[0]; p.dbg[6] = w_acc[1]; p.dbg[7] = w_acc[2]; }
+    if (warp == 8) p.dbg[8] = w_acc[0];
+    if (warp == 0) p.dbg[9] = n_kb;
   }
   // ---- teardown ----
   tc_fence_before();
@@ -583,6 +695,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
 
 constexpr size_t kUmmaSmem = 1024 + (size_t)kStagesDense * kStageBytes + 256;
 constexpr size_t kUmmaSmemCsr = 1024 + (size_t)kStagesCsr * kStageBytes + 256 + 2 * 128 * kRing * 4;
+constexpr size_t kUmmaSmemTma = 1024 + 2 * (size_t)kStageBytes + 256 + (size_t)kRawSlots * kRawBytes;
 
 template <int NACC>
 __global__ void __launch_bounds__(256)
@@ -660,15 +773,29 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   prm.ldP = ldP;
   prm.G = ctx->G;
   prm.flags = (int*)ctx->umma_flags.p;
+  const bool dbg = getenv("HS_UMMA_DEBUG") != nullptr;
+  prm.dbg = dbg ? (long long*)((char*)ctx->umma_flags.p + 64) : nullptr;
   dim3 grid(row_tiles, (unsigned)n_seg);
   if (perm) {
     HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModePerm>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
     k_dense_umma<kModePerm><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
+  } else if ((ld & 3) == 0 && (n_rows & 3) == 0 && (reinterpret_cast<uintptr_t>(e_dev) & 15) == 0 && !getenv("HS_DENSE_NO_TMA")) {
+    // every cell's run of rows is 16-byte aligned and sized: raw tiles can come through cp.async.bulk
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModeDenseTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemTma));
+    k_dense_umma<kModeDenseTma><<<grid, kUmmaThreads, kUmmaSmemTma, st>>>(prm);
   } else {
     HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModeDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmem));
     k_dense_umma<kModeDense><<<grid, kUmmaThreads, kUmmaSmem, st>>>(prm);
   }
   HS_LAUNCH_CHECK(ctx);
+  if (dbg) {
+    long long h[16] = {0};
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, prm.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[umma dbg] blocks %lld total %lld clk (%.0f/block) | producer: wait empty %lld, raw_full %lld | raw loader wait %lld | "
+                    "B loader wait %lld | mma: full_a %lld full_b %lld tmem_empty %lld | epilogue wait tmem_full %lld\n",
+            h[9], h[0], h[9] ? (double)h[0] / (double)h[9] : 0.0, h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8]);
+  }
   const unsigned eb = (unsigned)((n_rows + 7) / 8);
   k_p64_kl<4><<<eb, 256, 0, st>>>((const double*)ctx->part.p, (int)n_seg, seg_stride, n_rows, ldP, ctx->G, (const double*)ctx->Q.p,
                                   (const int*)ctx->umma_flags.p, out_dev);
