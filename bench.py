@@ -60,6 +60,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-f32", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--density-stage", dest="density_mode", default="broadcast", choices=["broadcast", "replicate"],
+                    help="N > 1: rank 0 runs the density stage and NCCL-broadcasts its state (default), or every rank "
+                         "recomputes it (deterministic kernels: identical bits)")
     ap.add_argument("--no-dense", action="store_true", help="skip the side measurement of the dense (tcgen05) kernel")
     ap.add_argument("--dense-genes", type=int, default=1024)
     ap.add_argument("--cpu-genes", type=int, default=24)
@@ -415,11 +418,21 @@ def run_b200(a):
 
     ev_k3 = []
 
+    ev_bc = []
+    ev_k4 = []
+
     def step(record: bool):
-        if world == 1 or rank == 0:
+        if world == 1 or rank == 0 or a.density_mode == "replicate":
             ctx.density_dev(x_dev, grid_dev)
-        if world > 1:
+        if world > 1 and a.density_mode == "broadcast":
+            b0 = b1 = None
+            if record:
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
             ctx.density_broadcast(n, g, src=0)
+            if record:
+                b1.record()
+                ev_bc.append((b0, b1))
         e0 = e1 = None
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -430,6 +443,10 @@ def run_b200(a):
             ev_k3.append((e0, e1))
         if n_sel_local:
             ctx.dkl_perm_csr_dev(gene_ptr, pval, pind, r_loc, dkl_rand, index_base=0)
+        if record:
+            e2 = torch.cuda.Event(enable_timing=True)
+            e2.record()
+            ev_k4.append((e1, e2))
         if world > 1:
             dist.all_gather_into_tensor(dkl_all, dkl)
 
@@ -461,6 +478,8 @@ def run_b200(a):
         ms_total = float(t.item())
     ms_step = ms_total / a.steps
     k3_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev_k3]))
+    bc_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev_bc])) if ev_bc else None
+    k4_ms = float(np.mean([e0.elapsed_time(e1) for e0, e1 in ev_k4]))
     value = m_total / (ms_step * 1e-3)
 
     # ---- roofline of the dominant kernel (K3 CSR contraction), algorithmic bytes per launch ----
@@ -505,7 +524,10 @@ def run_b200(a):
             "config": {"workload": workload_name(a), "cells": n, "genes_per_gpu": m_local, "genes_total": m_total,
                        "nnz_per_gpu": nnz, "grid_points": g, "dims": a.dims, "rand_genes": int(len(sel)),
                        "rand_count": a.rand_count, "l2": "inputs (CSR %.1f GB) larger than L2" % (8.0 * nnz / 1e9),
-                       "setup_s": round(setup_s, 1),
+                       "setup_s": round(setup_s, 1), "density_mode": a.density_mode if world > 1 else "single",
+                       "density_broadcast_ms_rank0": bc_ms,
+                       "rank0_ms": {"contraction": round(k3_ms, 3), "randomization": round(k4_ms, 3),
+                                    "randomized_rows": int(n_sel_local * r_loc)},
                        "parallelism": ("1 process per GPU, gene-sharded (30k genes each); K1 on rank 0 + NCCL broadcast of the "
                                        "density state; the S x R randomized rows are a fixed total, dealt to the ranks as "
                                        "(gene, 25-permutation) units balanced by nnz") if world > 1 else "1 GPU"},

@@ -112,33 +112,71 @@ __global__ void k_row_len(const int64_t* __restrict__ ptr, int64_t n_rows, int n
   rows[i] = (int32_t)i;
 }
 
+// Deal the length-sorted rows to the (tile, warp, slot) grid of the slab kernel.  The kernel ends with its
+// slowest CTA, and inside a CTA every slab ends with its slowest warp, so both levels are balanced:
+//  * tiles take every n_tiles-th rank, snaking (tile t gets rank j * n_tiles + t for even j, the mirrored
+//    one for odd j): every CTA sees the same cut through the length spectrum;
+//  * inside a tile the rows go, longest first, to the warp with the least entries so far that still has a
+//    free slot (greedy longest-processing-time).
+// One warp per tile; lane w keeps the running total of warp w.
+constexpr int kMaxTileRows = kMaxWarps * 17;
 template <bool PERM>
-__global__ void k_build_slots(const int64_t* __restrict__ ptr, const int32_t* __restrict__ sorted_rows,
-                              int64_t n_rows, int n_perm, int n_bins, int K, Slots sl) {
+__global__ void __launch_bounds__(32) k_build_slots(const int64_t* __restrict__ ptr, const int32_t* __restrict__ sorted_rows,
+                              int64_t n_rows, int n_perm, int n_tiles, int w_per_tile, int K, Slots sl) {
   // sorted_rows / n_rows: the (sub)range of the length-sorted row list this launch covers
-  const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot >= (int64_t)n_bins * K) return;
-  const int bin = (int)(slot / K), k = (int)(slot - (int64_t)bin * K);
-  const int64_t i = (int64_t)k * n_bins + ((k & 1) ? (n_bins - 1 - bin) : bin);   // snake deal
-  int64_t co = 0, vo = 0;
-  int32_t len = 0, row = -1;
-  if (i < n_rows) {
-    row = sorted_rows[i];
-    if (PERM) {
-      const int64_t s = row / n_perm, r = row - s * n_perm;
-      const int64_t g0 = ptr[s], nnz = ptr[s + 1] - g0;
-      co = g0 * n_perm + r * nnz;
-      vo = g0;
-      len = (int32_t)nnz;
-    } else {
-      co = vo = ptr[row];
-      len = (int32_t)(ptr[row + 1] - ptr[row]);
+  __shared__ int64_t s_co[kMaxTileRows], s_vo[kMaxTileRows];
+  __shared__ int32_t s_len[kMaxTileRows], s_row[kMaxTileRows];
+  const int tile = blockIdx.x, lane = threadIdx.x;
+  const int per_tile = w_per_tile * K;
+  for (int j = lane; j < per_tile; j += 32) {
+    const int64_t i = (int64_t)j * n_tiles + ((j & 1) ? (n_tiles - 1 - tile) : tile);
+    int64_t co = 0, vo = 0;
+    int32_t len = 0, row = -1;
+    if (i < n_rows) {
+      row = sorted_rows[i];
+      if (PERM) {
+        const int64_t s = row / n_perm, r = row - s * n_perm;
+        const int64_t g0 = ptr[s], nnz = ptr[s + 1] - g0;
+        co = g0 * n_perm + r * nnz;
+        vo = g0;
+        len = (int32_t)nnz;
+      } else {
+        co = vo = ptr[row];
+        len = (int32_t)(ptr[row + 1] - ptr[row]);
+      }
+    }
+    s_co[j] = co; s_vo[j] = vo; s_len[j] = len; s_row[j] = row;
+  }
+  __syncwarp();
+  int64_t load = 0;
+  int count = 0;
+  for (int j = 0; j < per_tile; ++j) {
+    if (s_row[j] < 0) continue;   // warp-uniform
+    // least-loaded warp with a free slot; ties to the lower warp
+    unsigned long long key = (lane < w_per_tile && count < K) ? (((unsigned long long)load << 5) | (unsigned)lane) : ~0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+      key = other < key ? other : key;
+    }
+    if ((int)(key & 31u) == lane) {
+      const int64_t slot = ((int64_t)tile * w_per_tile + lane) * K + count;
+      sl.coff[slot] = s_co[j];
+      sl.voff[slot] = s_vo[j];
+      sl.len[slot] = s_len[j];
+      sl.row[slot] = s_row[j];
+      load += s_len[j];
+      ++count;
     }
   }
-  sl.coff[slot] = co;
-  sl.voff[slot] = vo;
-  sl.len[slot] = len;
-  sl.row[slot] = row;
+  if (lane < w_per_tile)
+    for (int k = count; k < K; ++k) {
+      const int64_t slot = ((int64_t)tile * w_per_tile + lane) * K + k;
+      sl.coff[slot] = 0;
+      sl.voff[slot] = 0;
+      sl.len[slot] = 0;
+      sl.row[slot] = -1;
+    }
 }
 
 // rows (sorted by descending length) with at least `thr` stored entries -> out[0]
@@ -779,9 +817,9 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   sl.len = (int32_t*)w;                    w += slots4_b;
   sl.row = (int32_t*)w;                    w += slots4_b;
   if (perm)
-    k_build_slots<true><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out + n_dense, n_sub, n_perm, n_bins, K, sl);
+    k_build_slots<true><<<(unsigned)n_tiles, 32, 0, st>>>(ptr_dev, rows_out + n_dense, n_sub, n_perm, n_tiles, kWarps, K, sl);
   else
-    k_build_slots<false><<<(unsigned)((n_slots + tb - 1) / tb), tb, 0, st>>>(ptr_dev, rows_out + n_dense, n_sub, n_perm, n_bins, K, sl);
+    k_build_slots<false><<<(unsigned)n_tiles, 32, 0, st>>>(ptr_dev, rows_out + n_dense, n_sub, n_perm, n_tiles, kWarps, K, sl);
   HS_LAUNCH_CHECK(ctx);
 
   SpmmParams prm;
