@@ -609,7 +609,9 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     nnz_e = int(p_h[-1])
     # R hands over doubles (dgRMatrix@x); keep them in pinned memory as the contract asks
     vdt = torch.float64 if value_dtype == "float64" else torch.float32
-    vbytes = 8.0 if value_dtype == "float64" else 4.0
+    # fp64 host values are narrowed to fp32 by the library's host threads before they cross PCIe
+    # (HS_NARROW_ON_DEVICE=1 uploads the doubles instead): count the bytes that are actually copied
+    vbytes = 8.0 if (value_dtype == "float64" and os.environ.get("HS_NARROW_ON_DEVICE", "0") not in ("", "0")) else 4.0
     j_h = torch.empty(nnz_e, dtype=torch.int32).pin_memory()
     j_h.copy_(cols[:nnz_e])
     x_h = torch.empty(nnz_e, dtype=vdt).pin_memory()
@@ -655,6 +657,7 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     d2h = 8.0 * m_e2e + 8.0 * n_sel_local * r_loc + 8.0 * a.grid_points + 8.0
     return {"value": m_e2e * world / per, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": per * 1e3, "steps": a.e2e_steps, "genes_per_gpu": m_e2e,
+            "host_value_bytes": 8 if value_dtype == "float64" else 4, "pcie_value_bytes": int(vbytes),
             "note": (f"hs_density + hs_dkl_csr + hs_dkl_perm_csr with pinned host buffers ({value_dtype} values, int32 ids), "
                      "timed with the host clock around the blocking calls"
                      + ("" if m_e2e == m else f"; host memory limits the e2e pass to the first {m_e2e} genes"))}

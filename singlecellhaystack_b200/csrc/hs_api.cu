@@ -6,7 +6,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "hs_common.cuh"
@@ -51,6 +55,105 @@ int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes) {
   } else {
     b.cap = want;
   }
+  return HS_OK;
+}
+
+// ---- host worker threads ---------------------------------------------------------------------------
+// R hands the values over as doubles (dgRMatrix@x); the kernels read them as fp32.  Narrowing on the host
+// halves the bytes of the values on PCIe (the contraction of a 1M-cell matrix is transfer-bound end to end),
+// and is done by a few persistent threads into a pinned ring while earlier buffers are in flight.
+struct HostPool {
+  std::vector<std::thread> threads;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::function<void(int)> job;   // job(worker index)
+  uint64_t epoch = 0;
+  int pending = 0;
+  bool stop = false;
+
+  explicit HostPool(int n) {
+    for (int i = 0; i < n; ++i) threads.emplace_back([this, i] { loop(i); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv_work.notify_all();
+    for (auto& t : threads) t.join();
+  }
+  void loop(int idx) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(int)> fn;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return stop || epoch != seen; });
+        if (stop) return;
+        seen = epoch;
+        fn = job;
+      }
+      fn(idx);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (--pending == 0) cv_done.notify_all();
+      }
+    }
+  }
+  // runs fn(0 .. n_workers-1) on the workers and returns when all are done
+  void run(const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> lk(mu);
+    job = fn;
+    pending = (int)threads.size();
+    ++epoch;
+    cv_work.notify_all();
+    cv_done.wait(lk, [&] { return pending == 0; });
+  }
+  int size() const { return (int)threads.size(); }
+};
+
+static int host_threads() {
+  int n = (int)std::thread::hardware_concurrency();
+  if (n <= 0) n = 1;
+  n = std::min(n, 16);
+  if (const char* e = getenv("HS_HOST_THREADS")) {
+    const int v = atoi(e);
+    if (v > 0) n = std::min(v, 256);
+  }
+  return n;
+}
+
+// dst[i] = (float)src[i]; split over the pool when the block is large
+static void narrow_f64(hs_ctx* ctx, const double* src, float* dst, int64_t n) {
+  if (n < (int64_t)1 << 18 || host_threads() == 1) {
+    for (int64_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+    return;
+  }
+  if (!ctx->pool) ctx->pool = new HostPool(host_threads());
+  const int nt = ctx->pool->size();
+  const int64_t per = ((n + nt - 1) / nt + 15) & ~(int64_t)15;
+  ctx->pool->run([=](int t) {
+    const int64_t a = std::min<int64_t>(n, (int64_t)t * per), b = std::min<int64_t>(n, a + per);
+    for (int64_t i = a; i < b; ++i) dst[i] = (float)src[i];
+  });
+}
+
+static int ensure_ring(hs_ctx* ctx, size_t bytes) {
+  if (ctx->ring_cap >= bytes) return HS_OK;
+  for (int k = 0; k < hs_ctx::kRing; ++k) {
+    if (ctx->ring_busy[k]) {
+      HS_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[k]));
+      ctx->ring_busy[k] = false;
+    }
+    if (ctx->ring[k]) cudaFreeHost(ctx->ring[k]);
+    ctx->ring[k] = nullptr;
+  }
+  ctx->ring_cap = 0;
+  for (int k = 0; k < hs_ctx::kRing; ++k) {
+    HS_CUDA(ctx, cudaHostAlloc(&ctx->ring[k], bytes, cudaHostAllocDefault));
+    if (!ctx->ev_ring[k]) HS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ring[k], cudaEventDisableTiming));
+  }
+  ctx->ring_cap = bytes;
   return HS_OK;
 }
 
@@ -161,6 +264,11 @@ void hs_destroy(hs_ctx* ctx) {
                     &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (int k = 0; k < hs_ctx::kRing; ++k) {
+    if (ctx->ring[k]) cudaFreeHost(ctx->ring[k]);
+    if (ctx->ev_ring[k]) cudaEventDestroy(ctx->ev_ring[k]);
+  }
+  delete ctx->pool;
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   for (int i = 0; i < 2; ++i) {
@@ -335,7 +443,16 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   HS_TRY(hs_ensure(ctx, ctx->cols32, sizeof(int32_t) * (size_t)hs_max<int64_t>(n_ids, 1)));
   HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)hs_max<int64_t>(n_vals, 1)));
   const size_t stage_vals = (size_t)hs_min<int64_t>((int64_t)chunk, hs_max<int64_t>(n_vals, 1));
-  HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * stage_vals));
+  // fp64 values: narrowed on the host into a pinned ring (default), or uploaded as doubles and narrowed by
+  // a kernel (HS_NARROW_ON_DEVICE=1); both give the same fp32 bits
+  const bool narrow_on_device = env_size("HS_NARROW_ON_DEVICE", 0) != 0;
+  if (!vals_f32) {
+    if (narrow_on_device)
+      HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * stage_vals));
+    else
+      HS_TRY(ensure_ring(ctx, sizeof(float) * stage_vals));
+  }
+  int ring_k = 0;
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
 
   // row pointers rebased to the uploaded arrays
@@ -371,21 +488,40 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   for (size_t pc = 0; pc < piece_end.size(); ++pc) {
     const int64_t u1 = piece_end[pc];
     const int64_t a0 = rel[u0], a1 = rel[u1];
+    // Ids go straight into place; values are narrowed (fp64 sources) and follow.  The two are interleaved
+    // chunk by chunk so that the link always has an id chunk to move while the host narrows the matching
+    // values (the permutation form has few values and many ids: its ids go first, in pieces, so that
+    // pageable sources do not serialise one huge copy).
+    if (perm)
+      for (int64_t off = a0 * ipv; off < a1 * ipv; off += id_piece) {
+        const int64_t n = hs_min<int64_t>(id_piece, a1 * ipv - off);
+        HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 * ipv + off, sizeof(int32_t) * (size_t)n,
+                                     cudaMemcpyHostToDevice, cs));
+      }
     for (int64_t off = a0; off < a1; off += (int64_t)stage_vals) {
       const int64_t n = hs_min<int64_t>((int64_t)stage_vals, a1 - off);
+      if (!perm)
+        HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 + off, sizeof(int32_t) * (size_t)n,
+                                     cudaMemcpyHostToDevice, cs));
       if (vals_f32) {
         HS_CUDA(ctx, cudaMemcpyAsync((float*)ctx->vals32.p + off, vals32h + v0 + off, sizeof(float) * (size_t)n,
                                      cudaMemcpyHostToDevice, cs));
-      } else {
+      } else if (narrow_on_device) {
         HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
         HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p + off, n, cs));
+      } else {
+        const int k = ring_k;
+        ring_k = (ring_k + 1) % hs_ctx::kRing;
+        if (ctx->ring_busy[k]) {
+          HS_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[k]));
+          ctx->ring_busy[k] = false;
+        }
+        narrow_f64(ctx, vals + v0 + off, (float*)ctx->ring[k], n);
+        HS_CUDA(ctx, cudaMemcpyAsync((float*)ctx->vals32.p + off, ctx->ring[k], sizeof(float) * (size_t)n,
+                                     cudaMemcpyHostToDevice, cs));
+        HS_CUDA(ctx, cudaEventRecord(ctx->ev_ring[k], cs));
+        ctx->ring_busy[k] = true;
       }
-    }
-    // ids: straight into place, in pieces so that pageable sources do not serialise one huge copy
-    for (int64_t off = a0 * ipv; off < a1 * ipv; off += id_piece) {
-      const int64_t n = hs_min<int64_t>(id_piece, a1 * ipv - off);
-      HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 * ipv + off, sizeof(int32_t) * (size_t)n,
-                                   cudaMemcpyHostToDevice, cs));
     }
     HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[0], cs));
     HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[0], 0));

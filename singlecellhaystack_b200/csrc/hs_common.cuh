@@ -74,6 +74,13 @@ struct hs_ctx {
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, slab-bucketed (id, value) pairs
   void* pinned = nullptr;      // small pinned host bounce buffer
   size_t pinned_cap = 0;
+  // host-side fp64 -> fp32 narrowing of uploaded values (hs_api.cu): pinned ring + worker threads
+  static constexpr int kRing = 4;
+  void* ring[kRing] = {};
+  size_t ring_cap = 0;                                   // bytes per ring buffer
+  cudaEvent_t ev_ring[kRing] = {};   // the copy out of ring buffer k has finished
+  bool ring_busy[kRing] = {};
+  struct HostPool* pool = nullptr;
 };
 
 // ---- error helpers (host) -----------------------------------------------------------------
