@@ -39,6 +39,7 @@ if str(ROOT) not in sys.path:
 
 METRIC = "genes/sec incl. randomizations (1M cells, 100 grid pts)"
 UNIT = "genes/s"
+PERM_SEED = 20261019          # seed of the device-side randomization draw
 
 
 def parse_args():
@@ -63,6 +64,9 @@ def parse_args():
     ap.add_argument("--density-stage", dest="density_mode", default="broadcast", choices=["broadcast", "replicate"],
                     help="N > 1: rank 0 runs the density stage and NCCL-broadcasts its state (default), or every rank "
                          "recomputes it (deterministic kernels: identical bits)")
+    ap.add_argument("--perm-draw", default="device", choices=["device", "host"],
+                    help="randomization draw sample(n_cells, nnz) (R/haystack_continuous.R:275): made on the device "
+                         "from a seed (hs_dkl_perm_csr_seeded, default) or passed in as ids (hs_dkl_perm_csr)")
     ap.add_argument("--no-dense", action="store_true", help="skip the side measurement of the dense (tcgen05) kernel")
     ap.add_argument("--dense-genes", type=int, default=1024)
     ap.add_argument("--cpu-genes", type=int, default=24)
@@ -139,7 +143,7 @@ def row_stats_device(p, vals, n_cells: int):
     return (mean + 1e-300).cpu().numpy(), (sd + 1e-300).cpu().numpy()
 
 
-def make_perm_inputs_device(a, p, vals, sel_local, sel_global, perm_lo: int, perm_hi: int, dev):
+def make_perm_inputs_device(a, p, vals, sel_local, sel_global, perm_lo: int, perm_hi: int, dev, want_ids=True):
     """Stand-in for R's sample(x = count.cells, size = nnz) (:275): for every selected gene held by
     this rank, permutations perm_lo..perm_hi-1 as an nnz x R_local column-major int32 block of
     distinct 0-based cell ids (Feistel bijection of [0, N))."""
@@ -153,6 +157,8 @@ def make_perm_inputs_device(a, p, vals, sel_local, sel_global, perm_lo: int, per
         nnz = hi - lo
         gp.append(gp[-1] + nnz)
         val_parts.append(vals[lo:hi])
+        if not want_ids:
+            continue
         idx = torch.arange(nnz, device=dev, dtype=torch.int64)[None, :].expand(r_loc, nnz)
         stream = (int(gg) * 100003 + torch.arange(perm_lo, perm_hi, device=dev, dtype=torch.int64))[:, None].expand(r_loc, nnz)
         ids = synth.feistel_perm(synth.BASE_SEED, stream.contiguous(), idx.contiguous(), a.cells)
@@ -247,10 +253,11 @@ def cpu_sample_times(a, xs, grid, genes_rows, perm_gene, perm_ids1):
     t_gene = (time.perf_counter() - t0) / max(len(genes_rows), 1)
     nnz_sample = float(np.mean([len(v) for _, v in genes_rows])) if genes_rows else 0.0
     t0 = time.perf_counter()
-    for r in range(perm_ids1.shape[0]):
-        ho.get_D_KL_continuous_highD_SPARSE(perm_ids1[r], perm_gene, dens, q, ho.PSEUDO)
+    out_perm = [ho.get_D_KL_continuous_highD_SPARSE(perm_ids1[r], perm_gene, dens, q, ho.PSEUDO)
+                for r in range(perm_ids1.shape[0])]
     t_perm = (time.perf_counter() - t0) / max(perm_ids1.shape[0], 1)
-    return dict(t_density=t_density, t_gene=t_gene, t_perm=t_perm, nnz_sample=nnz_sample, dkl=np.array(out))
+    return dict(t_density=t_density, t_gene=t_gene, t_perm=t_perm, nnz_sample=nnz_sample, dkl=np.array(out),
+                dkl_perm=np.array(out_perm))
 
 
 def run_reference(a):
@@ -366,7 +373,8 @@ def run_b200(a):
     p_host = p.cpu().numpy()
     if world == 1:
         sel_local = sel.astype(np.int64)
-        gene_ptr, pval, pind, r_loc = make_perm_inputs_device(a, p_host, vals, sel_local, sel, 0, a.rand_count, dev)
+        gene_ptr, pval, pind, r_loc = make_perm_inputs_device(a, p_host, vals, sel_local, sel, 0, a.rand_count, dev,
+                                                              want_ids=a.perm_draw == "host")
         mine = np.arange(len(sel))
     else:
         # units = (selected gene, block of permutations), dealt to ranks by descending cost (LPT) so that the
@@ -396,6 +404,8 @@ def run_b200(a):
             nnz_g = int(v.numel())
             gp.append(gp[-1] + nnz_g)
             val_parts.append(v)
+            if a.perm_draw != "host":
+                continue
             idx = torch.arange(nnz_g, device=dev, dtype=torch.int64)[None, :].expand(r_loc, nnz_g)
             stream = (gid * 100003 + torch.arange(b * r_loc, (b + 1) * r_loc, device=dev, dtype=torch.int64))[:, None].expand(r_loc, nnz_g)
             ids = synth.feistel_perm(synth.BASE_SEED, stream.contiguous(), idx.contiguous(), a.cells)
@@ -419,6 +429,7 @@ def run_b200(a):
     ev_k3 = []
 
     ev_bc = []
+    perm_stream_base = rank << 40          # the ranks draw from disjoint streams
     ev_k4 = []
 
     def step(record: bool):
@@ -442,7 +453,10 @@ def run_b200(a):
             e1.record()
             ev_k3.append((e0, e1))
         if n_sel_local:
-            ctx.dkl_perm_csr_dev(gene_ptr, pval, pind, r_loc, dkl_rand, index_base=0)
+            if a.perm_draw == "device":
+                ctx.dkl_perm_csr_seeded_dev(gene_ptr, pval, r_loc, PERM_SEED, dkl_rand, stream_base=perm_stream_base)
+            else:
+                ctx.dkl_perm_csr_dev(gene_ptr, pval, pind, r_loc, dkl_rand, index_base=0)
         if record:
             e2 = torch.cuda.Event(enable_timing=True)
             e2.record()
@@ -598,7 +612,8 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     import torch.distributed as dist
     m = a.genes
     nnz = int(p[-1])
-    n_ind = int(pind.numel())
+    seeded = a.perm_draw == "device"
+    n_ind = 0 if seeded else int(pind.numel())
     need = 12.0 * nnz + 12.0 * int(pval.numel()) + 4.0 * n_ind
     avail = psutil.virtual_memory().available / max(world, 1)
     m_e2e = a.e2e_genes or m
@@ -620,7 +635,10 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     pv_h = torch.empty(int(pval.numel()), dtype=vdt).pin_memory()
     pv_h.copy_(pval.to(vdt))
     pi_h = torch.empty(n_ind, dtype=torch.int32).pin_memory()
-    pi_h.copy_(pind)
+    if not seeded:
+        pi_h.copy_(pind)
+    pv64 = pv_h.numpy().astype(np.float64) if seeded else None     # the seeded entry point takes doubles
+    perm_stream_base = rank << 40
     xs_h = torch.from_numpy(np.ascontiguousarray(xs.T)).pin_memory()       # column-major N x d
     grid_h = torch.from_numpy(np.ascontiguousarray(grid.T)).pin_memory()
     torch.cuda.synchronize()
@@ -635,7 +653,10 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
             ctx.density_broadcast(a.cells, a.grid_points, src=0)
         d = ctx.dkl_csr(p_np, j_np, x_np)
         if n_sel_local:
-            ctx.dkl_perm_csr_flat(gp_h, pv_h.numpy(), pi_h.numpy(), r_loc, index_base=0, out=out_rand)
+            if seeded:
+                ctx.dkl_perm_csr_seeded_flat(gp_h, pv64, r_loc, PERM_SEED, stream_base=perm_stream_base, out=out_rand)
+            else:
+                ctx.dkl_perm_csr_flat(gp_h, pv_h.numpy(), pi_h.numpy(), r_loc, index_base=0, out=out_rand)
         return d
 
     step()
@@ -658,7 +679,9 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
     return {"value": m_e2e * world / per, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "ms_per_step": per * 1e3, "steps": a.e2e_steps, "genes_per_gpu": m_e2e,
             "host_value_bytes": 8 if value_dtype == "float64" else 4, "pcie_value_bytes": int(vbytes),
-            "note": (f"hs_density + hs_dkl_csr + hs_dkl_perm_csr with pinned host buffers ({value_dtype} values, int32 ids), "
+            "perm_draw": a.perm_draw,
+            "note": (f"hs_density + hs_dkl_csr + {'hs_dkl_perm_csr_seeded' if seeded else 'hs_dkl_perm_csr'} with pinned host "
+                     f"buffers ({value_dtype} values, int32 ids), "
                      "timed with the host clock around the blocking calls"
                      + ("" if m_e2e == m else f"; host memory limits the e2e pass to the first {m_e2e} genes"))}
 
@@ -677,7 +700,11 @@ def run_cpu_baseline(a, xs, grid, p, cols, vals, dkl, gene_ptr, pval, pind, r_lo
         s = int(np.argmax(np.diff(gp) > 0)) if np.any(np.diff(gp) > 0) else 0
         nnz_s = int(gp[s + 1] - gp[s])
         pv = pval[gp[s]:gp[s + 1]].double().cpu().numpy()
-        blk = pind[gp[s] * r_loc: gp[s] * r_loc + nnz_s * r_loc].reshape(r_loc, nnz_s)[:k].cpu().numpy().astype(np.int64) + 1
+        if a.perm_draw == "device":    # the ids the device drew for (gene s, randomization r), restated on the CPU
+            from oracle import prp_oracle as po
+            blk = np.stack([po.prp_sample(PERM_SEED, s * r_loc + r, a.cells, nnz_s).astype(np.int64) for r in range(k)])
+        else:
+            blk = pind[gp[s] * r_loc: gp[s] * r_loc + nnz_s * r_loc].reshape(r_loc, nnz_s)[:k].cpu().numpy().astype(np.int64) + 1
     else:
         s, pv, blk = 0, rows[0][1], np.zeros((0, len(rows[0][1])), dtype=np.int64)
     tm = cpu_sample_times(a, xs, grid, rows, pv, blk)
@@ -687,6 +714,10 @@ def run_cpu_baseline(a, xs, grid, p, cols, vals, dkl, gene_ptr, pval, pind, r_lo
     got = dkl[pick].cpu().numpy()
     rel = float(np.max(np.abs(got - tm["dkl"]) / np.abs(tm["dkl"])))
     parity = {"genes_checked": int(len(pick)), "max_rel_err_dkl_vs_oracle": rel, "tolerance": 1e-5}
+    if n_sel_local and len(tm["dkl_perm"]):
+        got_p = dkl_rand.cpu().numpy().reshape(r_loc, n_sel_local)[:k, s]      # n_sel x R column-major
+        parity["randomized_rows_checked"] = int(k)
+        parity["max_rel_err_randomized_vs_oracle"] = float(np.max(np.abs(got_p - tm["dkl_perm"]) / np.abs(tm["dkl_perm"])))
     cpu = {"value": a.genes / total, "unit": UNIT, "cores": cores_used, "kind": "port",
            "sample": (f"fp64 NumPy oracle (restatement of R/haystack_continuous.R:168-186, :586-602; R itself is not "
                       f"installable here): density stage on {min(a.cells, a.cpu_density_cells)} cells, {len(rows)} genes "

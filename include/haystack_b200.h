@@ -13,6 +13,7 @@
  *                            get_D_KL_continuous_highD_SPARSE :586-602)
  *   hs_dkl_perm_dense     <- R/haystack_continuous.R:250-265  (dense randomization loop)
  *   hs_dkl_perm_csr       <- R/haystack_continuous.R:266-283  (sparse randomization loop)
+ *   hs_dkl_perm_csr_seeded<- the same loop including its sample() call (:275), drawn on the device
  *
  * Conventions
  *   - Plain C, POD arguments only.  No R, torch or CUDA types in any signature.
@@ -123,6 +124,21 @@ int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const d
 int hs_dkl_perm_csr_f32(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const float* val,
                         const int32_t* ind, int n_perm, int index_base, double* out);
 
+/* Sparse form with the draw made on the device.  Same scoring as hs_dkl_perm_csr, but instead of taking
+ * the ids of sample(x = n_cells, size = nnz_s) (R/haystack_continuous.R:275) from the caller, gene s /
+ * randomization r pairs val[gene_ptr[s] + i] with cell pi(i), i = 0 .. nnz_s-1, where pi is the keyed
+ * permutation of [0, n_cells) for (seed, stream_base + s * n_perm + r) defined in csrc/hs_prp.cuh
+ * (4-round Feistel network with cycle walking).  No ids cross PCIe, nothing is sorted, and repeated
+ * calls give bit-identical results.  hs_perm_sample returns the very ids a (seed, stream) draws, so a
+ * caller (or a test) can reproduce a randomization through hs_dkl_perm_csr.
+ * out is n_sel x n_perm column-major. */
+int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val,
+                           int n_perm, uint64_t seed, uint64_t stream_base, double* out);
+/* Host helper (no GPU involved): ids_out[i] = pi(i) + index_base for i < size, pi keyed by
+ * (seed, stream) over [0, n).  1 <= n < 2^31, 0 <= size <= n. */
+int hs_perm_sample(uint64_t seed, uint64_t stream, int64_t n, int64_t size, int index_base,
+                   int32_t* ids_out);
+
 /* ---- device-resident variants (inputs already in HBM; used by bench.py and by the
  *      multi-GPU host layer).  Pointers are device pointers in this process. --------------- */
 /* CSR with int64 row pointers, int32 0-based columns, fp32 values; dkl_dev_out fp64[n_genes]. */
@@ -130,6 +146,9 @@ int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, cons
                    int64_t n_genes, double* dkl_dev_out);
 /* gene_ptr_dev int64[n_sel+1], val_dev fp32, ind_dev int32 laid out as in hs_dkl_perm_csr;
  * out_dev fp64 n_sel x n_perm column-major. */
+int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
+                               const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base,
+                               double* out_dev);
 int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
                         const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base,
                         double* out_dev);

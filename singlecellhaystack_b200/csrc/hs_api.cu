@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "hs_common.cuh"
+#include "hs_prp.cuh"
 
 static thread_local std::string g_global_err;
 
@@ -699,6 +700,91 @@ int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, cons
   ScopedTimer tm(ctx, HS_T_CSR);
   HS_TRY(hs_run_csr(ctx, p_dev, j_dev, x_dev, n_genes, dkl_dev_out));
   tm.stop();
+  return HS_OK;
+}
+
+int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
+                               int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_sel < 0 || n_perm <= 0 || !gene_ptr_dev || !out_dev)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded_dev: bad arguments");
+  if (n_sel == 0) return HS_OK;
+  int64_t n_vals = 0;   // sizes the (cell, value) pair buffer
+  HS_CUDA(ctx, cudaMemcpyAsync(&n_vals, gene_ptr_dev + n_sel, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_vals < 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded_dev: gene_ptr is not a prefix sum");
+  if (n_vals > 0 && !val_dev) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded_dev: val is NULL");
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_seeded(ctx, gene_ptr_dev, n_sel, n_vals, val_dev, n_perm, seed, stream_base, out_dev));
+  tm.stop();
+  return HS_OK;
+}
+
+int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, int n_perm,
+                           uint64_t seed, uint64_t stream_base, double* out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_sel < 0 || n_perm <= 0 || !gene_ptr || !out)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded: bad arguments");
+  if (n_sel == 0) return HS_OK;
+  if (gene_ptr[0] != 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded: gene_ptr[0] must be 0");
+  for (int64_t i = 0; i < n_sel; ++i) {
+    if (gene_ptr[i + 1] < gene_ptr[i])
+      return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded: gene_ptr must be non-decreasing");
+    if (gene_ptr[i + 1] - gene_ptr[i] > ctx->N)
+      return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded: cannot take a sample larger than the population");
+  }
+  const int64_t n_vals = gene_ptr[n_sel];
+  if (n_vals > 0 && !val) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded: val is NULL");
+  // Only the values travel (n_vals floats), so memory is bounded by the pair buffer: split the genes into
+  // batches whose n_perm * nnz pairs fit.
+  size_t free_b = 0, total_b = 0;
+  HS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  free_b += ctx->perm_cols.cap + ctx->vals32.cap;
+  const double budget = (double)env_size("HS_UPLOAD_BUDGET", (size_t)(0.80 * (double)free_b));
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)(n_sel * n_perm)));
+  cudaStream_t st = ctx->stream;
+  std::vector<float> v32;
+  std::vector<double> tmp;
+  int64_t ub = 0;
+  while (ub < n_sel) {
+    int64_t ue = ub + 1;
+    while (ue < n_sel && (double)(gene_ptr[ue + 1] - gene_ptr[ub]) * (8.0 * n_perm + 4.0) <= budget) ++ue;
+    const int64_t v0 = gene_ptr[ub], nv = gene_ptr[ue] - v0, nu = ue - ub;
+    std::vector<int64_t> rel((size_t)nu + 1);
+    for (int64_t u = 0; u <= nu; ++u) rel[u] = gene_ptr[ub + u] - v0;
+    v32.resize((size_t)hs_max<int64_t>(nv, 1));
+    for (int64_t i = 0; i < nv; ++i) v32[i] = (float)val[v0 + i];
+    HS_TRY(hs_ensure(ctx, ctx->ptrs, sizeof(int64_t) * (size_t)(nu + 1)));
+    HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)hs_max<int64_t>(nv, 1)));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, rel.data(), sizeof(int64_t) * (size_t)(nu + 1), cudaMemcpyHostToDevice, st));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->vals32.p, v32.data(), sizeof(float) * (size_t)nv, cudaMemcpyHostToDevice, st));
+    double* dev_out = (double*)ctx->out.p + ub * n_perm;
+    ScopedTimer tm(ctx, HS_T_PERM);
+    HS_TRY(hs_run_perm_seeded(ctx, (const int64_t*)ctx->ptrs.p, nu, nv, (const float*)ctx->vals32.p, n_perm, seed,
+                              stream_base + (uint64_t)ub * (uint64_t)n_perm, dev_out));
+    tm.stop();
+    if (ub == 0 && ue == n_sel) {
+      HS_CUDA(ctx, cudaMemcpyAsync(out, dev_out, sizeof(double) * (size_t)(nu * n_perm), cudaMemcpyDeviceToHost, st));
+      HS_CUDA(ctx, cudaStreamSynchronize(st));
+    } else {   // batch-local nu x n_perm block -> its rows of the n_sel x n_perm result
+      tmp.resize((size_t)(nu * n_perm));
+      HS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), dev_out, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, st));
+      HS_CUDA(ctx, cudaStreamSynchronize(st));
+      for (int r = 0; r < n_perm; ++r)
+        for (int64_t s = 0; s < nu; ++s) out[(ub + s) + (int64_t)r * n_sel] = tmp[(size_t)s + (size_t)r * (size_t)nu];
+    }
+    ub = ue;
+  }
+  return HS_OK;
+}
+
+int hs_perm_sample(uint64_t seed, uint64_t stream, int64_t n, int64_t size, int index_base, int32_t* ids_out) {
+  if (n < 1 || n >= ((int64_t)1 << 31) || size < 0 || size > n || (size > 0 && !ids_out))
+    return hs_fail(nullptr, HS_ERR_INVALID, "hs_perm_sample: need 1 <= n < 2^31 and 0 <= size <= n");
+  const HsPrp prp = hs_prp_make(seed, stream, (uint32_t)n);
+  for (int64_t i = 0; i < size; ++i) ids_out[i] = (int32_t)((int64_t)hs_prp_forward(prp, (uint32_t)i) + index_base);
   return HS_OK;
 }
 

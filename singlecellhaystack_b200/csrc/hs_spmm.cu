@@ -17,12 +17,14 @@
 // Requirement: within a row the stored columns must be non-decreasing at slab granularity (Matrix
 // keeps dgRMatrix@j ascending).  Violations and negative ids are detected and flagged; the caller
 // then runs the order-independent gather kernel (hs_contract.cu) instead.
+#include <cub/block/block_radix_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include "hs_common.cuh"
+#include "hs_prp.cuh"
 
 namespace {
 
@@ -872,6 +874,184 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
 // Randomization batch, sparse form: bucket every permuted row by slab, then run the slab kernel over
 // the n_sel * n_perm rows.  Returns HS_ERR_STATE-free HS_OK, or a negative "not applicable" marker (-1)
 // when the cell axis has too many slabs for the shared-memory histogram (the caller then gathers).
+// ---- K4-sparse, seeded form: draw the permutations on the device, already ordered by cell ---------------
+// One CTA per permuted row walks the cells in order; a thread takes kGenPerThread consecutive cells, asks the
+// row's keyed permutation for i = pi^-1(c) and keeps the cell when i < nnz, paired with the gene's i-th value
+// (hs_prp.cuh).  A block-wide scan turns the keep counts into output positions, so the (cell, value) pairs
+// come out ascending by cell: exactly what the slab kernel wants, with no ids uploaded and nothing sorted,
+// and the fp32 summation order of a row is fixed (bit-identical repeats).
+constexpr int kGenThreads = 256;
+constexpr int kGenPerThread = 8;
+
+__global__ void __launch_bounds__(kGenThreads)
+k_perm_generate(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
+                const float* __restrict__ val, int64_t N, uint64_t seed, uint64_t stream_base, int small_max,
+                uint2* __restrict__ out) {
+  __shared__ unsigned int s_warp[kGenThreads / 32];
+  __shared__ unsigned int s_total, s_cnt;
+  __shared__ uint2 s_list[kGenThreads * kGenPerThread];      // (value to walk on, slot) of the cells that left the domain
+  __shared__ uint32_t s_res[kGenThreads * kGenPerThread];
+  const int64_t row = blockIdx.x;
+  const int64_t s = row / n_perm;
+  const int64_t g0 = gp[s];
+  const uint32_t nnz = (uint32_t)(gp[s + 1] - g0);
+  if (nnz <= (uint32_t)small_max) return;   // empty, or drawn forward by k_perm_generate_small
+  const HsPrp prp = hs_prp_make(seed, stream_base + (uint64_t)row, (uint32_t)N);
+  uint2* dst = out + rp[row];
+  const float* v = val + g0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned int running = 0;
+  const uint32_t n32 = (uint32_t)N;
+  for (uint32_t c0 = 0; c0 < n32; c0 += kGenThreads * kGenPerThread) {
+    const uint32_t cb = c0 + threadIdx.x * kGenPerThread;
+    uint32_t idx[kGenPerThread];
+    // One decryption per cell.  The few results outside [0, N) (the network's domain is a power of four)
+    // must be decrypted again until they fall inside; a per-thread loop would make every warp pay a second
+    // pass for its one or two stragglers, so they are queued and finished by the first threads of the block.
+    unsigned int walk = 0;
+    if (c0 + kGenThreads * kGenPerThread <= n32) {   // whole chunk inside the population (block-uniform)
+#pragma unroll
+      for (int j = 0; j < kGenPerThread; ++j) {
+        idx[j] = hs_prp_dec1(prp, cb + j);
+        walk |= (idx[j] >= n32 ? 1u : 0u) << j;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kGenPerThread; ++j) {
+        idx[j] = 0xffffffffu;
+        if (cb + j < n32) {
+          idx[j] = hs_prp_dec1(prp, cb + j);
+          walk |= (idx[j] >= n32 ? 1u : 0u) << j;
+        }
+      }
+    }
+    if (walk) {
+      unsigned int q = atomicAdd(&s_cnt, (unsigned int)__popc(walk));
+#pragma unroll
+      for (int j = 0; j < kGenPerThread; ++j)
+        if ((walk >> j) & 1u) s_list[q++] = make_uint2(idx[j], threadIdx.x * kGenPerThread + j);
+    }
+    __syncthreads();
+    for (unsigned int t = threadIdx.x; t < s_cnt; t += kGenThreads) {
+      const uint2 e = s_list[t];
+      uint32_t x = e.x;
+      do x = hs_prp_dec1(prp, x); while (x >= n32);
+      s_res[e.y] = x;
+    }
+    __syncthreads();
+    unsigned int keep = 0;
+#pragma unroll
+    for (int j = 0; j < kGenPerThread; ++j) {
+      if ((walk >> j) & 1u) idx[j] = s_res[threadIdx.x * kGenPerThread + j];
+      keep += idx[j] < nnz;
+    }
+    // exclusive scan of `keep` over the block, in thread order
+    unsigned int incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned int w = lane < kGenThreads / 32 ? s_warp[lane] : 0u;
+      unsigned int wi = w;
+#pragma unroll
+      for (int o = 1; o < kGenThreads / 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += t;
+      }
+      if (lane < kGenThreads / 32) s_warp[lane] = wi - w;
+      if (lane == kGenThreads / 32 - 1) s_total = wi;
+      if (lane == 0) s_cnt = 0;
+    }
+    __syncthreads();
+    unsigned int pos = running + s_warp[warp] + incl - keep;
+    running += s_total;
+#pragma unroll
+    for (int j = 0; j < kGenPerThread; ++j)
+      if (idx[j] < nnz) dst[pos++] = make_uint2(cb + j, __float_as_uint(__ldg(v + idx[j])));
+    // (the next chunk rewrites s_warp / s_total only after two more block-wide barriers)
+  }
+}
+
+// Rows with few stored values: walking all N cells for a handful of draws is wasteful, so these rows draw
+// forward (pi(0 .. nnz-1), one thread per few draws) and a block-wide radix sort orders the pairs by cell.
+// Same set of pairs in the same (ascending) order as k_perm_generate would emit.
+constexpr int kSmallThreads = 512;
+constexpr int kSmallItems = 16;
+constexpr int kSmallRowMax = kSmallThreads * kSmallItems;   // 8192 stored values
+using SmallSort = cub::BlockRadixSort<uint32_t, kSmallThreads, kSmallItems, uint32_t>;
+
+__global__ void __launch_bounds__(kSmallThreads)
+k_perm_generate_small(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
+                      const float* __restrict__ val, int64_t N, uint64_t seed, uint64_t stream_base,
+                      uint2* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  SmallSort::TempStorage& tmp = *reinterpret_cast<SmallSort::TempStorage*>(sort_smem);
+  const int64_t row = blockIdx.x;
+  const int64_t s = row / n_perm;
+  const int64_t g0 = gp[s];
+  const int64_t nnz64 = gp[s + 1] - g0;
+  if (nnz64 == 0 || nnz64 > kSmallRowMax) return;
+  const uint32_t nnz = (uint32_t)nnz64;
+  const HsPrp prp = hs_prp_make(seed, stream_base + (uint64_t)row, (uint32_t)N);
+  uint32_t keys[kSmallItems], vals[kSmallItems];
+#pragma unroll
+  for (int k = 0; k < kSmallItems; ++k) {
+    const uint32_t i = threadIdx.x * kSmallItems + k;
+    keys[k] = 0xffffffffu;   // padding sorts to the end
+    vals[k] = 0u;
+    if (i < nnz) {
+      keys[k] = hs_prp_forward(prp, i);
+      vals[k] = __float_as_uint(__ldg(val + g0 + i));
+    }
+  }
+  SmallSort(tmp).Sort(keys, vals);
+  uint2* dst = out + rp[row];
+#pragma unroll
+  for (int k = 0; k < kSmallItems; ++k) {
+    const uint32_t i = threadIdx.x * kSmallItems + k;
+    if (i < nnz) dst[i] = make_uint2(keys[k], vals[k]);
+  }
+}
+
+int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
+                       const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev) {
+  const int64_t n_rows = n_sel * (int64_t)n_perm;
+  if (n_rows <= 0) return HS_OK;
+  if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many randomized rows in one call");
+  if (hs_slab_cells(ctx) < 4)
+    return hs_fail(ctx, HS_ERR_INVALID, "seeded randomization: the density rows do not fit the slab kernel");
+  const int64_t n_ids = n_vals_total * n_perm;
+  HS_TRY(hs_ensure(ctx, ctx->perm_rp, sizeof(int64_t) * (size_t)(n_rows + 1)));
+  HS_TRY(hs_ensure(ctx, ctx->perm_cols, sizeof(uint2) * (size_t)hs_max<int64_t>(n_ids, 1)));   // (cell, value) pairs
+  cudaStream_t st = ctx->stream;
+  int64_t* rp = (int64_t*)ctx->perm_rp.p;
+  k_perm_row_ptr<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(gene_ptr_dev, n_sel, n_perm, rp);
+  HS_LAUNCH_CHECK(ctx);
+  // every row is offered to both kernels; each takes the rows of its size class and leaves the others
+  int small_max = kSmallRowMax;
+  if (const char* e = getenv("HS_PERM_SMALL_ROW")) small_max = hs_max(0, hs_min(atoi(e), kSmallRowMax));
+  if (small_max > 0) {
+    const size_t sm = sizeof(SmallSort::TempStorage);
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_perm_generate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k_perm_generate_small<<<(unsigned)n_rows, kSmallThreads, sm, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ctx->N, seed,
+                                                                     stream_base, (uint2*)ctx->perm_cols.p);
+    HS_LAUNCH_CHECK(ctx);
+  }
+  k_perm_generate<<<(unsigned)n_rows, kGenThreads, 0, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ctx->N, seed, stream_base,
+                                                            small_max, (uint2*)ctx->perm_cols.p);
+  HS_LAUNCH_CHECK(ctx);
+  const int* flag = nullptr;
+  HS_TRY(hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
+                          /*allow_umma=*/false, &flag, ctx->perm_cols.p));
+  return HS_OK;
+}
+
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
   const int64_t n_rows = n_sel * (int64_t)n_perm;

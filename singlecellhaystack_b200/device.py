@@ -48,6 +48,18 @@ def _wrap_device_ptr(ptr: int, nbytes: int, dev):
     return torch.as_tensor(_Cai(), device=dev)
 
 
+def perm_sample(seed: int, stream: int, n: int, size: int, index_base: int = 1) -> np.ndarray:
+    """hs_perm_sample: the `size` cell ids (index_base-based, in draw order) that the seeded randomization
+    entry points pair with a gene's values for (seed, stream).  Host-only; stands in for
+    sample(x = n, size = size) (R/haystack_continuous.R:275)."""
+    lib = _lib.load()
+    out = np.empty(int(size), dtype=np.int32)
+    rc = lib.hs_perm_sample(int(seed) % (1 << 64), int(stream) % (1 << 64), int(n), int(size), int(index_base), _ptr(out))
+    if rc != _lib.HS_OK:
+        raise ValueError(f"hs_perm_sample failed ({rc}): {_lib.last_error(None)}")
+    return out
+
+
 class DeviceContext:
     """Owns an `hs_ctx*`.  Not thread-safe (neither is R, the intended caller)."""
 
@@ -248,6 +260,35 @@ class DeviceContext:
                                               _ptr(out)), "hs_dkl_perm_csr")
         return out
 
+    def dkl_perm_csr_seeded(self, vals: list, n_perm: int, seed: int, stream_base: int = 0) -> np.ndarray:
+        """hs_dkl_perm_csr_seeded: like dkl_perm_csr, but gene s / randomization r draws its cells on the
+        device from the keyed permutation (seed, stream_base + s * n_perm + r); `perm_sample` returns the
+        same ids on the host.  Returns (S, R)."""
+        s_ = len(vals)
+        if s_ == 0:
+            return np.zeros((0, 0))
+        gp = np.zeros(s_ + 1, dtype=np.int64)
+        for i, v in enumerate(vals):
+            gp[i + 1] = gp[i] + len(v)
+        val = np.concatenate([np.asarray(v, dtype=np.float64) for v in vals]) if gp[-1] else np.zeros(0)
+        out = np.empty((s_, int(n_perm)), dtype=np.float64, order="F")
+        self._check(self._lib.hs_dkl_perm_csr_seeded(self._h, _ptr(gp), s_, _ptr(val), int(n_perm),
+                                                     int(seed) % (1 << 64), int(stream_base) % (1 << 64), _ptr(out)),
+                    "hs_dkl_perm_csr_seeded")
+        return out
+
+    def dkl_perm_csr_seeded_flat(self, gene_ptr, val, n_perm, seed, stream_base=0, out=None) -> np.ndarray:
+        """hs_dkl_perm_csr_seeded on flattened host arrays (gene_ptr int64 [S+1], val fp64)."""
+        gene_ptr = np.ascontiguousarray(gene_ptr, dtype=np.int64)
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        s_ = gene_ptr.size - 1
+        if out is None:
+            out = np.empty((s_, int(n_perm)), dtype=np.float64, order="F")
+        self._check(self._lib.hs_dkl_perm_csr_seeded(self._h, _ptr(gene_ptr), s_, _ptr(val), int(n_perm),
+                                                     int(seed) % (1 << 64), int(stream_base) % (1 << 64), _ptr(out)),
+                    "hs_dkl_perm_csr_seeded")
+        return out
+
     def dkl_perm_csr_flat(self, gene_ptr, val, ind, n_perm, index_base=1, out=None) -> np.ndarray:
         """hs_dkl_perm_csr on already flattened host arrays (gene_ptr int64 [S+1], val fp64, ind int32
         laid out gene by gene as nnz_s x n_perm column-major blocks).  No host-side copies."""
@@ -275,6 +316,12 @@ class DeviceContext:
         self._check(self._lib.hs_dkl_perm_csr_dev(self._h, _dptr(gene_ptr_dev), s_, _dptr(val_dev), _dptr(ind_dev),
                                                   int(n_perm), int(index_base), _dptr(out_dev)),
                     "hs_dkl_perm_csr_dev")
+
+    def dkl_perm_csr_seeded_dev(self, gene_ptr_dev, val_dev, n_perm, seed, out_dev, stream_base=0):
+        s_ = gene_ptr_dev.numel() - 1
+        self._check(self._lib.hs_dkl_perm_csr_seeded_dev(self._h, _dptr(gene_ptr_dev), s_, _dptr(val_dev), int(n_perm),
+                                                         int(seed) % (1 << 64), int(stream_base) % (1 << 64),
+                                                         _dptr(out_dev)), "hs_dkl_perm_csr_seeded_dev")
 
     def dkl_dense_dev(self, expr_dev, n_genes, ld, out_dev):
         self._check(self._lib.hs_dkl_dense_dev(self._h, _dptr(expr_dev), int(n_genes), int(ld), _dptr(out_dev)),

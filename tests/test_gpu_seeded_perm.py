@@ -1,0 +1,118 @@
+"""Seeded randomization batch (hs_dkl_perm_csr_seeded): the device draws sample(n_cells, nnz)
+(R/haystack_continuous.R:275) from the keyed permutation; parity against the fp64 oracle fed with the same
+ids (oracle/prp_oracle.py), and against the ids-given entry point."""
+import numpy as np
+import pytest
+
+from oracle import haystack_oracle as ho
+from oracle import prp_oracle as po
+from singlecellhaystack_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL_DKL = 1e-5
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def _toy_rows(toy, k):
+    expr = toy["expression"]
+    sp = ho.RowSparse.from_dense(expr)
+    genes = toy["full_genes_to_randomize"][:k]
+    return [ho.extract_row_dgRMatrix_as_sparse(sp, int(g) + 1)[1] for g in genes], expr.shape[1]
+
+
+@pytest.mark.parametrize("g", [60, 100])
+def test_seeded_matches_oracle_on_toy(ctx, toy, g):
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ref = ho.density_stage(xs, toy[f"grid{g}"])
+    ctx.density(xs, toy[f"grid{g}"])
+    vals, n = _toy_rows(toy, 10)
+    n_perm, seed, base = 40, 424242, 1000
+    inds = [np.stack([po.prp_sample(seed, base + s * n_perm + r, n, v.size) for r in range(n_perm)])
+            for s, v in enumerate(vals)]                                          # (R, nnz) 1-based
+    want = ho.dkl_randomized_sparse(vals, inds, ref["density"], ref["Q"])
+    got = ctx.dkl_perm_csr_seeded(vals, n_perm, seed, stream_base=base)
+    assert got.shape == (10, n_perm)
+    assert _rel(got, want) < RTOL_DKL
+    # the ids-given entry point on the very same draw
+    via_ids = ctx.dkl_perm_csr(vals, [np.asfortranarray(a.T) for a in inds], index_base=1)
+    assert _rel(got, via_ids) < 1e-6
+    # bit-identical when repeated, and when the genes are scored in two calls with shifted streams
+    again = ctx.dkl_perm_csr_seeded(vals, n_perm, seed, stream_base=base)
+    np.testing.assert_array_equal(got, again)
+    lo = ctx.dkl_perm_csr_seeded(vals[:4], n_perm, seed, stream_base=base)
+    hi = ctx.dkl_perm_csr_seeded(vals[4:], n_perm, seed, stream_base=base + 4 * n_perm)
+    np.testing.assert_array_equal(got, np.vstack([lo, hi]))
+
+
+def test_seeded_edge_rows(ctx, toy):
+    """Empty gene, single stored value, and a gene stored in every cell (the draw is a full permutation)."""
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ref = ho.density_stage(xs, toy["grid60"])
+    ctx.density(xs, toy["grid60"])
+    n = 601
+    rng = np.random.default_rng(3)
+    vals = [np.zeros(0), np.array([2.5]), rng.random(n) + 0.1, rng.random(17)]
+    n_perm, seed = 7, 5
+    got = ctx.dkl_perm_csr_seeded(vals, n_perm, seed)
+    inds = [np.stack([po.prp_sample(seed, s * n_perm + r, n, v.size) for r in range(n_perm)]) if v.size
+            else np.zeros((n_perm, 0), dtype=np.int32) for s, v in enumerate(vals)]
+    want = ho.dkl_randomized_sparse(vals[1:], inds[1:], ref["density"], ref["Q"])
+    assert _rel(got[1:], want) < RTOL_DKL
+    # a gene without stored values: P is the pseudocount only, i.e. uniform over the grid points
+    q = ref["Q"]
+    assert np.allclose(got[0], np.sum(np.full(60, 1 / 60) * np.log(np.full(60, 1 / 60) / q)), rtol=1e-9)
+    # every cell drawn: any permutation of a full row of constant values scores the same
+    full = ctx.dkl_perm_csr_seeded([np.ones(n)], 5, 11)
+    assert np.ptp(full) < 1e-12 * np.abs(full).max()
+
+
+def test_seeded_oversized_sample_is_rejected(ctx, toy):
+    from singlecellhaystack_b200.device import HaystackLibraryError
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ctx.density(xs, toy["grid60"])
+    with pytest.raises(HaystackLibraryError, match="larger than the population"):
+        ctx.dkl_perm_csr_seeded([np.ones(602)], 3, 1)
+
+
+def test_seeded_batches_and_large_population(ctx):
+    """A population that is not a power of two (cycle walking), genes split into memory batches."""
+    import os
+    n, d, g = 70001, 6, 48
+    x, _ = synth.make_embedding(n, d, seed=77)
+    xs, _, _ = ho.scale_coords(x)
+    grid = synth.make_grid(xs, g, seed=77)
+    ref = ho.density_stage(xs, grid)
+    ctx.density(xs, grid)
+    rng = np.random.default_rng(8)
+    vals = [rng.gamma(2.0, 1.0, size=int(k)) for k in (5, 900, 23000, 70001, 3100, 1)]
+    n_perm, seed = 6, 2026
+    got = ctx.dkl_perm_csr_seeded(vals, n_perm, seed)
+    inds = [np.stack([po.prp_sample(seed, s * n_perm + r, n, v.size) for r in range(n_perm)]) for s, v in enumerate(vals)]
+    want = ho.dkl_randomized_sparse(vals, inds, ref["density"], ref["Q"])
+    assert _rel(got, want) < RTOL_DKL
+    os.environ["HS_UPLOAD_BUDGET"] = str(2_000_000)      # forces several batches
+    try:
+        split = ctx.dkl_perm_csr_seeded(vals, n_perm, seed)
+    finally:
+        del os.environ["HS_UPLOAD_BUDGET"]
+    np.testing.assert_array_equal(got, split)
+
+
+def test_short_and_long_row_kernels_agree(ctx, toy):
+    """Rows with few stored values are drawn forward and sorted; the others walk the cells through the
+    inverse permutation.  Both emit the same pairs in the same order, so the scores are bit-identical."""
+    import os
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ctx.density(xs, toy["grid100"])
+    vals, _ = _toy_rows(toy, 12)
+    a = ctx.dkl_perm_csr_seeded(vals, 9, 77)
+    os.environ["HS_PERM_SMALL_ROW"] = "0"            # everything through the cell walk
+    try:
+        b = ctx.dkl_perm_csr_seeded(vals, 9, 77)
+    finally:
+        del os.environ["HS_PERM_SMALL_ROW"]
+    np.testing.assert_array_equal(a, b)
