@@ -151,7 +151,10 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
     reference's; the keyword-only ones are host plumbing:
       gene_names   row names of `expression` (R takes them from rownames())
       rng          seed or numpy Generator for every random draw (R: set.seed())
-      perm_source  callable(kind, gene0, n, size, count) -> (count, size) 1-based ids, replaces sample()
+      perm_source  callable(kind, gene0, n, size, count) -> (count, size) 1-based ids, replaces sample();
+                   or the string "device" (sparse input): the draws are made on the GPU from a seed taken
+                   from `rng` (hs_dkl_perm_csr_seeded; stream = position in genes_to_randomize *
+                   randomization_count + r, reproducible on the host with device.perm_sample)
       cv_folds     (folds_for_mean_model, folds_for_sd_model) replacing sample(rep(1:10, ...))
       row_stats    (mean, sd) per gene computed by the caller (the R shim passes R's own
                    Matrix::rowMeans / rowSds, so the integer gene selection is R's even for tied genes)
@@ -288,11 +291,20 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         _message(verbose, "### performing randomizations...")
         genes_to_randomize = select_genes_to_randomize(coeffVar, n_genes_to_randomize,
                                                        selection_method_genes_to_randomize)
-        src = perm_source if perm_source is not None else _NumpyPermSource(rng)
+        info_perm_seed = None
+        device_draw = isinstance(perm_source, str)
+        if device_draw and perm_source != "device":
+            raise ValueError("perm_source must be a callable, None or 'device'")
+        src = None if device_draw else (perm_source if perm_source is not None else _NumpyPermSource(rng))
 
         # ---- K4: randomized D_KL (:245-284); draws in the reference's order (gene-major) ---
         all_D_KL_randomized = np.full((n_genes_to_randomize, randomization_count), np.nan)
-        if sparse_in:
+        if sparse_in and device_draw:
+            perm_seed = int(rng.integers(0, 2 ** 63))
+            vals = [_sparse.extract_row_dgRMatrix_as_sparse(expression, int(g) + 1)["val"] for g in genes_to_randomize]
+            all_D_KL_randomized[:, :] = ctx.dkl_perm_csr_seeded(vals, randomization_count, perm_seed)
+            info_perm_seed = perm_seed
+        elif sparse_in:
             budget = 64 << 20          # ids per device call
             batch_vals, batch_inds, batch_rows, used = [], [], [], 0
 
@@ -314,6 +326,8 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
                     flush()
             flush()
         else:
+            if device_draw:
+                src = _NumpyPermSource(rng)     # the dense form has no seeded entry point yet
             for i, g in enumerate(genes_to_randomize):
                 perms = src("dense", int(g), count_cells, count_cells, randomization_count)       # (R, N)
                 all_D_KL_randomized[i, :] = ctx.dkl_perm_dense(expression[int(g)],
@@ -334,6 +348,8 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
     rand_info["method"] = spline_method
     rand_info["genes_to_randomize"] = genes_to_randomize + 1          # 1-based, as R stores them
     rand_info["KLD_rand"] = all_D_KL_randomized
+    if info_perm_seed is not None:
+        rand_info["perm_seed"] = info_perm_seed      # device.perm_sample(perm_seed, i * R + r, N, nnz) reproduces a draw
     p_vals = pv["fitted"]
     p_adjs = p_vals + math.log10(p_vals.size) if p_vals.size else p_vals.copy()
     p_adjs = np.where(p_adjs > 0, 0.0, p_adjs)

@@ -230,3 +230,36 @@ def test_zero_variance_genes_are_filtered(ctx, toy):
                           gene_names=list(toy["gene_names"]))
     assert res["results"].shape == (498, 3)
     assert "gene_4" not in res["results"].index and "gene_11" not in res["results"].index
+
+
+def test_toy_full_path_with_device_draws(ctx, toy):
+    """perm_source="device": the randomization draws are made on the GPU from a seed.  The whole result must
+    equal the oracle's when the oracle is fed the very ids that seed yields (oracle/prp_oracle.py), and the
+    p-values must agree with the host-drawn run within what 100 randomizations can resolve."""
+    from oracle import prp_oracle as po
+    seed = int(toy["seed"])
+    coord, expr = toy["coord"], toy["expression"]
+    stats = ho.row_mean_sd(ho.RowSparse.from_dense(expr))
+    folds = (synth.cv_folds(seed, 0, 100), synth.cv_folds(seed, 1, 100))
+    kw = dict(grid_coord=toy["grid100"], gene_names=list(toy["gene_names"]), row_stats=stats, cv_folds=folds,
+              ctx=ctx, verbose=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = hh.haystack(coord, sp.as_CsparseMatrix(expr), perm_source="device", rng=123, **kw)
+        res2 = hh.haystack(coord, sp.as_CsparseMatrix(expr), perm_source="device", rng=123, **kw)
+    rnd = res["info"]["randomization"]
+    perm_seed = rnd["perm_seed"]
+    np.testing.assert_array_equal(rnd["KLD_rand"], res2["info"]["randomization"]["KLD_rand"])   # reproducible
+    np.testing.assert_array_equal(rnd["genes_to_randomize"], toy["full_genes_to_randomize"] + 1)
+
+    def oracle_src(kind, gene, n, size, count):
+        i = int(np.nonzero(toy["full_genes_to_randomize"] == gene)[0][0])
+        return np.stack([po.prp_sample(perm_seed, i * count + r, n, size) for r in range(count)])
+
+    want = ho.haystack_continuous_highD(coord, ho.RowSparse.from_dense(expr), toy["grid100"], oracle_src, folds[0], folds[1])
+    assert _rel(rnd["KLD_rand"], want["KLD_rand"]) < RTOL_DKL
+    assert np.max(np.abs(res["results"]["log.p.vals"].values - want["log_p_vals"])) < ATOL_LOGP
+    # same null distribution as the host-drawn golden run: per-gene means within a few standard errors
+    gold = toy["full_KLD_rand"]
+    z = (rnd["KLD_rand"].mean(axis=1) - gold.mean(axis=1)) / (gold.std(axis=1, ddof=1) * np.sqrt(2 / 100))
+    assert np.abs(z).max() < 5 and abs(z.mean()) < 0.5
