@@ -35,7 +35,9 @@ b200_dkl_csr <- function(dev, expression) {          # expression: dgRMatrix
   .Call("hsb_dkl_csr", dev, expression@p, expression@j, expression@x, PACKAGE = "haystackB200")
 }
 
-b200_randomize <- function(dev, expression, genes.to.randomize, randomization.count, count.cells) {
+b200_randomize <- function(dev, expression, genes.to.randomize, randomization.count, count.cells,
+                           draw = c("R", "device"), seed = sample.int(.Machine$integer.max, 1)) {
+  draw <- match.arg(draw)
   n.sel <- length(genes.to.randomize)
   if (is.matrix(expression)) {
     out <- matrix(NA_real_, n.sel, randomization.count)
@@ -46,6 +48,17 @@ b200_randomize <- function(dev, expression, genes.to.randomize, randomization.co
       out[i, ] <- .Call("hsb_dkl_perm_dense", dev, as.double(v), perm, PACKAGE = "haystackB200")
     }
     return(out)
+  }
+  if (draw == "device") {
+    # the library draws sample(x = count.cells, size = nnz) itself (keyed permutation, stream =
+    # (i - 1) * randomization.count + r - 1); b200_perm_sample() returns the ids of any one draw
+    vals <- lapply(genes.to.randomize, function(g) {
+      lo <- expression@p[g] + 1L; hi <- expression@p[g + 1L]
+      if (hi >= lo) expression@x[lo:hi] else numeric(0)
+    })
+    gene.ptr <- c(0, cumsum(vapply(vals, length, 0)))
+    return(.Call("hsb_dkl_perm_csr_seeded", dev, as.double(gene.ptr), unlist(vals),
+                 as.integer(randomization.count), as.double(seed), PACKAGE = "haystackB200"))
   }
   vals <- vector("list", n.sel); inds <- vector("list", n.sel)
   for (i in seq_len(n.sel)) {
@@ -61,3 +74,6 @@ b200_randomize <- function(dev, expression, genes.to.randomize, randomization.co
   .Call("hsb_dkl_perm_csr", dev, as.double(gene.ptr), unlist(vals), unlist(inds),
         as.integer(randomization.count), PACKAGE = "haystackB200")
 }
+
+b200_perm_sample <- function(seed, stream, n, size)
+  .Call("hsb_perm_sample", as.double(seed), as.double(stream), as.double(n), as.double(size), PACKAGE = "haystackB200")

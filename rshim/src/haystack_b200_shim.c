@@ -108,6 +108,33 @@ SEXP hsb_dkl_perm_csr(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP ind, SEXP n_perm)
   return out;
 }
 
+/* Seeded form: the draws of R/haystack_continuous.R:275 are made on the device.  seed: numeric(1) holding
+ * a non-negative integer < 2^53 (e.g. sample.int(.Machine$integer.max, 1)). */
+SEXP hsb_dkl_perm_csr_seeded(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP n_perm, SEXP seed) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t s = XLENGTH(gene_ptr) - 1;
+  const int r = asInteger(n_perm);
+  int64_t* gp = (int64_t*)R_alloc((size_t)s + 1, sizeof(int64_t));
+  for (int64_t i = 0; i <= s; ++i) gp[i] = (int64_t)REAL(gene_ptr)[i];
+  SEXP out = PROTECT(allocMatrix(REALSXP, (int)s, r));
+  check(ctx, hs_dkl_perm_csr_seeded(ctx, gp, s, REAL(val), r, (uint64_t)asReal(seed), 0, REAL(out)),
+        "hs_dkl_perm_csr_seeded");
+  UNPROTECT(1);
+  return out;
+}
+
+/* ids of one draw (1-based), for reproducing a seeded randomization in R */
+SEXP hsb_perm_sample(SEXP seed, SEXP stream, SEXP n, SEXP size) {
+  const int64_t k = (int64_t)asReal(size);
+  SEXP out = PROTECT(allocVector(INTSXP, (R_xlen_t)k));
+  if (hs_perm_sample((uint64_t)asReal(seed), (uint64_t)asReal(stream), (int64_t)asReal(n), k, 1, INTEGER(out)) != HS_OK) {
+    UNPROTECT(1);
+    Rf_error("hs_perm_sample: %s", hs_last_error(NULL));
+  }
+  UNPROTECT(1);
+  return out;
+}
+
 static const R_CallMethodDef call_methods[] = {
     {"hsb_create", (DL_FUNC)&hsb_create, 1},
     {"hsb_density", (DL_FUNC)&hsb_density, 5},
@@ -115,6 +142,8 @@ static const R_CallMethodDef call_methods[] = {
     {"hsb_dkl_csr", (DL_FUNC)&hsb_dkl_csr, 4},
     {"hsb_dkl_perm_dense", (DL_FUNC)&hsb_dkl_perm_dense, 3},
     {"hsb_dkl_perm_csr", (DL_FUNC)&hsb_dkl_perm_csr, 5},
+    {"hsb_dkl_perm_csr_seeded", (DL_FUNC)&hsb_dkl_perm_csr_seeded, 5},
+    {"hsb_perm_sample", (DL_FUNC)&hsb_perm_sample, 4},
     {NULL, NULL, 0}};
 
 void R_init_haystackB200(DllInfo* dll) {
