@@ -785,18 +785,41 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
 
   // ---- the remaining rows: slab kernel ----
   const int64_t n_sub = n_rows - n_dense;
-  const Shape shp = pick_shape(NV, hs_max<int64_t>(n_sub, 1), sms);
+  // Tiling.  A CTA streams its whole cell segment through shared memory whatever its rows need (a slab
+  // fill takes ~5 us), so a tile must hold enough rows (~48 at 10 % density) for the contraction, not the
+  // streaming, to set the pace.  With many rows: whole waves of CTAs, rows dealt evenly (slots may stay
+  // empty).  With few rows: fewer, taller tiles, and the cell axis split over grid.y so that the machine
+  // is still full (5000 rows: 74 tiles x 2 segments instead of 148 tiles of 34 rows).
+  const int64_t total_slabs = (ctx->N + S - 1) / S;
+  int min_tile_rows = 48;
+  if (const char* e = getenv("HS_SLAB_MIN_TILE_ROWS")) min_tile_rows = hs_max(1, atoi(e));
+  const Shape big = pick_shape(NV, (int64_t)1 << 40, sms);            // the largest shape of this NV
+  min_tile_rows = hs_min(min_tile_rows, big.k * big.w);
+  Shape shp;
+  int n_tiles, n_seg = 1;
+  if (n_sub >= (int64_t)sms * min_tile_rows) {
+    shp = pick_shape(NV, hs_max<int64_t>(n_sub, 1), sms);
+    const int64_t per_wave = (int64_t)shp.w * shp.k * sms;
+    const int64_t waves = hs_max<int64_t>(1, (n_sub + per_wave - 1) / per_wave);
+    n_tiles = (int)hs_max<int64_t>(1, hs_min<int64_t>(waves * sms, n_sub));
+  } else {
+    const int max_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms, total_slabs / 4));
+    int best_seg = 1;
+    for (int sg = 1; sg <= max_seg; ++sg) {
+      const int64_t tiles = hs_max<int64_t>(1, hs_min<int64_t>(sms / sg, n_sub));
+      const int64_t rows_per_tile = (hs_max<int64_t>(n_sub, 1) + tiles - 1) / tiles;
+      if (rows_per_tile > (int64_t)big.k * big.w) break;
+      best_seg = sg;
+      if (rows_per_tile >= min_tile_rows || tiles == 1) break;
+    }
+    n_seg = best_seg;
+    n_tiles = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms / n_seg, n_sub));
+    const int64_t rows_per_tile = (hs_max<int64_t>(n_sub, 1) + n_tiles - 1) / n_tiles;
+    shp = pick_shape(NV, rows_per_tile, 1);                             // smallest shape that holds a tile
+  }
   const int K = shp.k, kWarps = shp.w;
-  // whole waves of CTAs: rows are dealt evenly over waves * sms tiles (slots may stay empty), but a
-  // tile never holds less than one row per warp
-  const int64_t waves = hs_max<int64_t>(1, (n_sub + (int64_t)kWarps * K * sms - 1) / ((int64_t)kWarps * K * sms));
-  const int n_tiles = (int)hs_max<int64_t>(1, hs_min<int64_t>(waves * sms, (n_sub + kWarps - 1) / kWarps));
   const int n_bins = n_tiles * kWarps;
   const int64_t n_slots = (int64_t)n_bins * K;
-  // split the cell axis over grid.y when there are too few row tiles to fill the machine
-  int n_seg = 1;
-  const int64_t total_slabs = (ctx->N + S - 1) / S;
-  if (n_tiles * 2 <= sms) n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(sms / n_tiles, total_slabs / 4));
   const int64_t seg_cells = ((total_slabs + n_seg - 1) / n_seg) * S;
   n_seg = (int)((ctx->N + seg_cells - 1) / seg_cells);
   // fp64 column sums: one [n_rows][ldP] block per cell segment of either kernel (single writer per block
