@@ -14,6 +14,7 @@
  *   hs_dkl_perm_dense     <- R/haystack_continuous.R:250-265  (dense randomization loop)
  *   hs_dkl_perm_csr       <- R/haystack_continuous.R:266-283  (sparse randomization loop)
  *   hs_dkl_perm_csr_seeded<- the same loop including its sample() call (:275), drawn on the device
+ *   hs_dkl_perm_dense_seeded <- the dense loop including its sample() call (:259), drawn on the device
  *
  * Conventions
  *   - Plain C, POD arguments only.  No R, torch or CUDA types in any signature.
@@ -134,6 +135,11 @@ int hs_dkl_perm_csr_f32(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, con
  * out is n_sel x n_perm column-major. */
 int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val,
                            int n_perm, uint64_t seed, uint64_t stream_base, double* out);
+/* Dense form with the draw made on the device: randomization r scores v[pi_r(c)] at cell c, pi_r keyed by
+ * (seed, stream_base + r) -- sample(x = v) == v[sample.int(n_cells)] (R/haystack_continuous.R:259) without the
+ * n_cells x n_perm index matrix.  hs_perm_sample(seed, stream_base + r, n_cells, n_cells, ...) returns pi_r. */
+int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t seed, uint64_t stream_base,
+                             double* out);
 /* Host helper (no GPU involved): ids_out[i] = pi(i) + index_base for i < size, pi keyed by
  * (seed, stream) over [0, n).  1 <= n < 2^31, 0 <= size <= n. */
 int hs_perm_sample(uint64_t seed, uint64_t stream, int64_t n, int64_t size, int index_base,
@@ -149,6 +155,8 @@ int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, cons
 int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
                                const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base,
                                double* out_dev);
+int hs_dkl_perm_dense_seeded_dev(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed,
+                                 uint64_t stream_base, double* out_dev);
 int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
                         const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base,
                         double* out_dev);

@@ -828,5 +828,37 @@ int hs_dkl_perm_dense_dev(hs_ctx* ctx, const float* v_dev, const int32_t* perm_d
   return HS_OK;
 }
 
+int hs_dkl_perm_dense_seeded_dev(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed, uint64_t stream_base,
+                                 double* out_dev) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (!v_dev || !out_dev || n_perm <= 0)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense_seeded_dev: bad arguments");
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_dense_seeded(ctx, v_dev, n_perm, seed, stream_base, out_dev));
+  tm.stop();
+  return HS_OK;
+}
+
+int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t seed, uint64_t stream_base,
+                             double* out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (!v || !out || n_perm <= 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense_seeded: bad arguments");
+  const int64_t N = ctx->N;
+  HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)n_perm));
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, v, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, st));
+  HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p, N, st));
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_dense_seeded(ctx, (const float*)ctx->vals32.p, n_perm, seed, stream_base, (double*)ctx->out.p));
+  tm.stop();
+  HS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, sizeof(double) * (size_t)n_perm, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

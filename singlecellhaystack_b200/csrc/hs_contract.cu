@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include "hs_common.cuh"
+#include "hs_prp.cuh"
 
 namespace {
 
@@ -354,4 +355,30 @@ int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, 
     if (rc != HS_OK && rc != -1) return rc;
   }
   return launch_dense<float, true>(ctx, (const float*)nullptr, 0, v_dev, perm_dev, index_base, n_perm, flag, out_dev);
+}
+
+
+// ---- K4-dense, seeded form ---------------------------------------------------------------------------
+// sample(x = row) == row[sample.int(N)] (R/haystack_continuous.R:259): randomization r reads cell pi_r(c) for
+// cell c, pi_r the keyed permutation of (seed, stream_base + r) (hs_prp.cuh).  The ids are written once into
+// device scratch (N x n_perm int32, 0-based) and scored by the ids-given kernels, so the tensor-core path,
+// its overflow fallback and the G > 128 kernel are shared; what the seeded form removes is the 4 N n_perm
+// bytes per gene that would otherwise cross PCIe (400 MB at 1M cells x 100 randomizations).
+__global__ void __launch_bounds__(256)
+k_perm_ids_dense(int64_t N, uint64_t seed, uint64_t stream_base, int32_t* __restrict__ perm) {
+  const int r = blockIdx.y;
+  const HsPrp prp = hs_prp_make(seed, stream_base + (uint64_t)r, (uint32_t)N);
+  for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < N; c += (int64_t)gridDim.x * blockDim.x)
+    perm[c + (int64_t)r * N] = (int32_t)hs_prp_forward(prp, (uint32_t)c);
+}
+
+int hs_run_perm_dense_seeded(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed, uint64_t stream_base,
+                             double* out_dev) {
+  const int64_t N = ctx->N;
+  HS_TRY(hs_ensure(ctx, ctx->stage_j[1], sizeof(int32_t) * (size_t)N * (size_t)n_perm));
+  int32_t* ids = (int32_t*)ctx->stage_j[1].p;
+  const unsigned bx = (unsigned)hs_min<int64_t>((N + 255) / 256, 4096);
+  k_perm_ids_dense<<<dim3(bx, (unsigned)n_perm), 256, 0, ctx->stream>>>(N, seed, stream_base, ids);
+  HS_LAUNCH_CHECK(ctx);
+  return hs_run_perm_dense(ctx, v_dev, ids, n_perm, 0, out_dev);
 }

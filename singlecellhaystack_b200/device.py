@@ -240,6 +240,18 @@ class DeviceContext:
                     "hs_dkl_perm_dense")
         return out
 
+    def dkl_perm_dense_seeded(self, v, n_perm: int, seed: int, stream_base: int = 0) -> np.ndarray:
+        """hs_dkl_perm_dense_seeded: randomization r scores v[pi_r], pi_r = perm_sample(seed, stream_base + r,
+        N, N) drawn on the device.  Returns (R,)."""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        if v.shape != (self.shape[0],):
+            raise ValueError("v must have length n_cells")
+        out = np.empty(int(n_perm), dtype=np.float64)
+        self._check(self._lib.hs_dkl_perm_dense_seeded(self._h, _ptr(v), int(n_perm), int(seed) % (1 << 64),
+                                                       int(stream_base) % (1 << 64), _ptr(out)),
+                    "hs_dkl_perm_dense_seeded")
+        return out
+
     def dkl_perm_csr(self, vals: list, inds: list, index_base=1) -> np.ndarray:
         """vals[s]: (nnz_s,) values of selected gene s; inds[s]: (nnz_s, R) column r =
         sample(n_cells, nnz_s).  Returns (S, R) (all.D_KL.randomized)."""
@@ -326,6 +338,11 @@ class DeviceContext:
     def dkl_dense_dev(self, expr_dev, n_genes, ld, out_dev):
         self._check(self._lib.hs_dkl_dense_dev(self._h, _dptr(expr_dev), int(n_genes), int(ld), _dptr(out_dev)),
                     "hs_dkl_dense_dev")
+
+    def dkl_perm_dense_seeded_dev(self, v_dev, n_perm, seed, out_dev, stream_base=0):
+        self._check(self._lib.hs_dkl_perm_dense_seeded_dev(self._h, _dptr(v_dev), int(n_perm), int(seed) % (1 << 64),
+                                                           int(stream_base) % (1 << 64), _dptr(out_dev)),
+                    "hs_dkl_perm_dense_seeded_dev")
 
     def dkl_perm_dense_dev(self, v_dev, perm_dev, n_perm, out_dev, index_base=0):
         self._check(self._lib.hs_dkl_perm_dense_dev(self._h, _dptr(v_dev), _dptr(perm_dev), int(n_perm),

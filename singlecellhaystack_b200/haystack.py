@@ -152,9 +152,10 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
       gene_names   row names of `expression` (R takes them from rownames())
       rng          seed or numpy Generator for every random draw (R: set.seed())
       perm_source  callable(kind, gene0, n, size, count) -> (count, size) 1-based ids, replaces sample();
-                   or the string "device" (sparse input): the draws are made on the GPU from a seed taken
-                   from `rng` (hs_dkl_perm_csr_seeded; stream = position in genes_to_randomize *
-                   randomization_count + r, reproducible on the host with device.perm_sample)
+                   or the string "device": the draws are made on the GPU from a seed taken from `rng`
+                   (hs_dkl_perm_csr_seeded / hs_dkl_perm_dense_seeded; stream = position in
+                   genes_to_randomize * randomization_count + r, reproducible on the host with
+                   device.perm_sample)
       cv_folds     (folds_for_mean_model, folds_for_sd_model) replacing sample(rep(1:10, ...))
       row_stats    (mean, sd) per gene computed by the caller (the R shim passes R's own
                    Matrix::rowMeans / rowSds, so the integer gene selection is R's even for tied genes)
@@ -325,9 +326,13 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
                 if used >= budget:
                     flush()
             flush()
+        elif device_draw:
+            perm_seed = int(rng.integers(0, 2 ** 63))
+            for i, g in enumerate(genes_to_randomize):
+                all_D_KL_randomized[i, :] = ctx.dkl_perm_dense_seeded(expression[int(g)], randomization_count, perm_seed,
+                                                                      stream_base=i * randomization_count)
+            info_perm_seed = perm_seed
         else:
-            if device_draw:
-                src = _NumpyPermSource(rng)     # the dense form has no seeded entry point yet
             for i, g in enumerate(genes_to_randomize):
                 perms = src("dense", int(g), count_cells, count_cells, randomization_count)       # (R, N)
                 all_D_KL_randomized[i, :] = ctx.dkl_perm_dense(expression[int(g)],

@@ -116,3 +116,43 @@ def test_short_and_long_row_kernels_agree(ctx, toy):
     finally:
         del os.environ["HS_PERM_SMALL_ROW"]
     np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("g", [60, 100])
+def test_seeded_dense_matches_oracle_on_toy(ctx, toy, g):
+    """Dense form: sample(x = row) == row[sample.int(N)] (R/haystack_continuous.R:259) drawn on the device."""
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ref = ho.density_stage(xs, toy[f"grid{g}"])
+    ctx.density(xs, toy[f"grid{g}"])
+    expr = toy["expression"]
+    n = expr.shape[1]
+    n_perm, seed = 30, 99
+    for k, gidx in enumerate(toy["full_genes_to_randomize"][:4]):
+        base = k * n_perm
+        perms = np.stack([po.prp_sample(seed, base + r, n, n) for r in range(n_perm)])          # (R, N) 1-based
+        want = ho.dkl_randomized_dense(expr[[gidx]], perms[None], ref["density"], ref["Q"])[0]
+        got = ctx.dkl_perm_dense_seeded(expr[gidx], n_perm, seed, stream_base=base)
+        assert _rel(got, want) < RTOL_DKL
+        via_ids = ctx.dkl_perm_dense(expr[gidx], np.asfortranarray(perms.T), index_base=1)
+        np.testing.assert_array_equal(got, via_ids)          # same ids, same kernels
+        np.testing.assert_array_equal(got, ctx.dkl_perm_dense_seeded(expr[gidx], n_perm, seed, stream_base=base))
+
+
+def test_dense_front_door_with_device_draws(ctx, toy):
+    import warnings
+    from singlecellhaystack_b200 import haystack as hh
+    seed = int(toy["seed"])
+    coord, expr = toy["coord"], toy["expression"]
+    stats = ho.row_mean_sd(expr)
+    folds = (synth.cv_folds(seed, 0, 20), synth.cv_folds(seed, 1, 20))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = hh.haystack(coord, expr, grid_coord=toy["grid100"], perm_source="device", rng=5, row_stats=stats,
+                          cv_folds=folds, ctx=ctx, verbose=False, n_genes_to_randomize=20, randomization_count=25)
+    rnd = res["info"]["randomization"]
+    ps = rnd["perm_seed"]
+    ref = ho.density_stage(ho.scale_coords(coord)[0], toy["grid100"])
+    g0 = int(rnd["genes_to_randomize"][3]) - 1
+    perms = np.stack([po.prp_sample(ps, 3 * 25 + r, 601, 601) for r in range(25)])
+    want = ho.dkl_randomized_dense(expr[[g0]], perms[None], ref["density"], ref["Q"])[0]
+    assert _rel(rnd["KLD_rand"][3], want) < RTOL_DKL
