@@ -43,6 +43,11 @@ b200_randomize <- function(dev, expression, genes.to.randomize, randomization.co
     out <- matrix(NA_real_, n.sel, randomization.count)
     for (i in seq_len(n.sel)) {
       v <- expression[genes.to.randomize[i], ]
+      if (draw == "device") {
+        out[i, ] <- .Call("hsb_dkl_perm_dense_seeded", dev, as.double(v), as.integer(randomization.count),
+                          as.double(seed), as.double((i - 1) * randomization.count), PACKAGE = "haystackB200")
+        next
+      }
       # sample(x = v) == v[sample.int(length(v))]: same RNG consumption as the reference (:259)
       perm <- vapply(seq_len(randomization.count), function(r) sample.int(count.cells), integer(count.cells))
       out[i, ] <- .Call("hsb_dkl_perm_dense", dev, as.double(v), perm, PACKAGE = "haystackB200")

@@ -123,6 +123,17 @@ SEXP hsb_dkl_perm_csr_seeded(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP n_perm, SE
   return out;
 }
 
+/* Dense seeded form: R/haystack_continuous.R:259 drawn on the device; stream_base = (i - 1) * R for gene i */
+SEXP hsb_dkl_perm_dense_seeded(SEXP sctx, SEXP v, SEXP n_perm, SEXP seed, SEXP stream_base) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int r = asInteger(n_perm);
+  SEXP out = PROTECT(allocVector(REALSXP, r));
+  check(ctx, hs_dkl_perm_dense_seeded(ctx, REAL(v), r, (uint64_t)asReal(seed), (uint64_t)asReal(stream_base), REAL(out)),
+        "hs_dkl_perm_dense_seeded");
+  UNPROTECT(1);
+  return out;
+}
+
 /* ids of one draw (1-based), for reproducing a seeded randomization in R */
 SEXP hsb_perm_sample(SEXP seed, SEXP stream, SEXP n, SEXP size) {
   const int64_t k = (int64_t)asReal(size);
@@ -143,6 +154,7 @@ static const R_CallMethodDef call_methods[] = {
     {"hsb_dkl_perm_dense", (DL_FUNC)&hsb_dkl_perm_dense, 3},
     {"hsb_dkl_perm_csr", (DL_FUNC)&hsb_dkl_perm_csr, 5},
     {"hsb_dkl_perm_csr_seeded", (DL_FUNC)&hsb_dkl_perm_csr_seeded, 5},
+    {"hsb_dkl_perm_dense_seeded", (DL_FUNC)&hsb_dkl_perm_dense_seeded, 5},
     {"hsb_perm_sample", (DL_FUNC)&hsb_perm_sample, 4},
     {NULL, NULL, 0}};
 
