@@ -172,6 +172,18 @@ int hs_density_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims
                    const double* grid_dev, int n_grid, const double* w_q_dev,
                    double* bandwidth_out, double* q_out);
 
+/* ---- row statistics (the step before the path; optional) ----------------------------------- */
+/* Matrix::rowMeans and the per-row sample sd (n-1 denominator, implicit zeros counted) of a CSR matrix --
+ * R/haystack_continuous.R:57-74, the inputs of coeffVar (:222) and of the gene selection (:227-236).  Two
+ * passes in fp64 on the device; the doubles are uploaded as they are (the result feeds an integer decision).
+ * Needs no density state.  mean_out / sd_out: n_genes doubles each, WITHOUT the +1e-300 of :82-83. */
+int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, int64_t n_genes,
+                     int64_t n_cells, double* mean_out, double* sd_out);
+/* Same on the fp32 values already resident for hs_dkl_csr_dev (statistics of the narrowed values:
+ * relative differences of order 1e-8 from the above). */
+int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_genes,
+                         int64_t n_cells, double* mean_dev, double* sd_dev);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Number of kernels of this library launched on this context since creation. */
 int64_t hs_launch_count(const hs_ctx* ctx);

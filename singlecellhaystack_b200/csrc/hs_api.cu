@@ -860,5 +860,73 @@ int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t 
   return HS_OK;
 }
 
+int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_genes, int64_t n_cells,
+                         double* mean_dev, double* sd_dev) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || n_cells < 1 || !p_dev || !mean_dev || !sd_dev)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_row_stats_csr_dev: bad arguments");
+  return hs_run_row_stats_f32(ctx, p_dev, x_dev, n_genes, n_cells, mean_dev, sd_dev);
+}
+
+int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, int64_t n_genes, int64_t n_cells,
+                     double* mean_out, double* sd_out) {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || n_cells < 1 || !p || !mean_out || !sd_out)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_row_stats_csr: bad arguments");
+  if (n_genes == 0) return HS_OK;
+  std::vector<int64_t> hp((size_t)n_genes + 1);
+  for (int64_t i = 0; i <= n_genes; ++i) hp[i] = p_is_64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
+  int64_t longest = 0;
+  for (int64_t i = 0; i < n_genes; ++i) {
+    if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_row_stats_csr: row pointers must be non-decreasing");
+    longest = hs_max(longest, hp[i + 1] - hp[i]);
+  }
+  if (hp[n_genes] > hp[0] && !x) return hs_fail(ctx, HS_ERR_INVALID, "hs_row_stats_csr: x is NULL");
+  // The doubles travel as they are (the statistics feed an integer decision, the gene selection): pieces of
+  // whole rows through two staging buffers, so the upload of one piece overlaps the passes over the other.
+  const int64_t piece_vals = hs_max<int64_t>(longest, (int64_t)env_size("HS_STAGE_VALUES", (size_t)16 << 20));
+  std::vector<int64_t> first;          // first row of every piece (+ n_genes at the end)
+  for (int64_t u0 = 0; u0 < n_genes;) {
+    int64_t u1 = u0 + 1;
+    while (u1 < n_genes && hp[u1 + 1] - hp[u0] <= piece_vals) ++u1;
+    first.push_back(u0);
+    u0 = u1;
+  }
+  first.push_back(n_genes);
+  const size_t n_pieces = first.size() - 1;
+  // row pointers relative to each piece's first value; piece pc owns slots [first[pc] + pc, first[pc+1] + pc]
+  std::vector<int64_t> pall((size_t)n_genes + n_pieces);
+  for (size_t pc = 0; pc < n_pieces; ++pc)
+    for (int64_t u = first[pc]; u <= first[pc + 1]; ++u) pall[(size_t)u + pc] = hp[u] - hp[first[pc]];
+  for (int b = 0; b < 2; ++b) HS_TRY(hs_ensure(ctx, ctx->stage_x[b], sizeof(double) * (size_t)hs_max<int64_t>(piece_vals, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->ptrs, sizeof(int64_t) * pall.size()));
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(double) * (size_t)(2 * n_genes)));
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  double* mean_dev = (double*)ctx->out.p;
+  double* sd_dev = mean_dev + n_genes;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, pall.data(), sizeof(int64_t) * pall.size(), cudaMemcpyHostToDevice, st));
+  HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
+  HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));   // earlier work on the staging buffers is done
+  for (size_t pc = 0; pc < n_pieces; ++pc) {
+    const int64_t r0 = first[pc], r1 = first[pc + 1];
+    const int bsel = (int)(pc & 1);
+    const int64_t nv = hp[r1] - hp[r0];
+    if (pc >= 2) HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[bsel], 0));
+    if (nv > 0)
+      HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[bsel].p, x + hp[r0], sizeof(double) * (size_t)nv, cudaMemcpyHostToDevice, cs));
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[bsel], cs));
+    HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[bsel], 0));
+    HS_TRY(hs_run_row_stats_f64(ctx, (const int64_t*)ctx->ptrs.p + r0 + (int64_t)pc, (const double*)ctx->stage_x[bsel].p,
+                                r1 - r0, n_cells, mean_dev + r0, sd_dev + r0));
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[bsel], st));
+  }
+  HS_CUDA(ctx, cudaMemcpyAsync(mean_out, mean_dev, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaMemcpyAsync(sd_out, sd_dev, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+}
+
 }  // extern "C"
 #pragma GCC visibility pop

@@ -122,6 +122,10 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
                      const void* pairs_dev = nullptr);
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
+int hs_run_row_stats_f64(hs_ctx* ctx, const int64_t* p_dev, const double* x_dev, int64_t n_rows, int64_t n_cells,
+                         double* mean_dev, double* sd_dev);
+int hs_run_row_stats_f32(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_rows, int64_t n_cells,
+                         double* mean_dev, double* sd_dev);
 int hs_run_perm_dense_seeded(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed, uint64_t stream_base,
                              double* out_dev);
 int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,

@@ -382,3 +382,51 @@ int hs_run_perm_dense_seeded(hs_ctx* ctx, const float* v_dev, int n_perm, uint64
   HS_LAUNCH_CHECK(ctx);
   return hs_run_perm_dense(ctx, v_dev, ids, n_perm, 0, out_dev);
 }
+
+
+// ---- row statistics (R/haystack_continuous.R:57-74) --------------------------------------------------
+// Matrix::rowMeans and the per-row sample standard deviation (n - 1 denominator, the implicit zeros of the
+// sparse row counted), the inputs of coeffVar and of the integer gene selection (:222-236).  Two passes in
+// fp64, one warp per row: mean = sum(x) / N, then ss = sum((x - mean)^2) + (N - nnz) * mean^2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_row_stats_csr(const int64_t* __restrict__ p, const T* __restrict__ x, int64_t n_rows, int64_t n_cells,
+                double* __restrict__ mean_out, double* __restrict__ sd_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int64_t lo = p[row], hi = p[row + 1];
+  double s = 0.0;
+  for (int64_t i = lo + lane; i < hi; i += 32) s += (double)x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const double mean = s / (double)n_cells;
+  double ss = 0.0;
+  for (int64_t i = lo + lane; i < hi; i += 32) {
+    const double d = (double)x[i] - mean;
+    ss += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) {
+    ss += (double)(n_cells - (hi - lo)) * mean * mean;
+    mean_out[row] = mean;
+    sd_out[row] = n_cells > 1 ? sqrt(ss / (double)(n_cells - 1)) : nan("");
+  }
+}
+
+int hs_run_row_stats_f64(hs_ctx* ctx, const int64_t* p_dev, const double* x_dev, int64_t n_rows, int64_t n_cells,
+                         double* mean_dev, double* sd_dev) {
+  if (n_rows <= 0) return HS_OK;
+  k_row_stats_csr<double><<<(unsigned)((n_rows + 7) / 8), 256, 0, ctx->stream>>>(p_dev, x_dev, n_rows, n_cells, mean_dev, sd_dev);
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
+
+int hs_run_row_stats_f32(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_rows, int64_t n_cells,
+                         double* mean_dev, double* sd_dev) {
+  if (n_rows <= 0) return HS_OK;
+  k_row_stats_csr<float><<<(unsigned)((n_rows + 7) / 8), 256, 0, ctx->stream>>>(p_dev, x_dev, n_rows, n_cells, mean_dev, sd_dev);
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}

@@ -127,6 +127,24 @@ class DeviceContext:
         self._check(self._lib.hs_density_shape(self._h, C.byref(n), C.byref(g)), "hs_density_shape")
         return int(n.value), int(g.value)
 
+    # -- row statistics (R/haystack_continuous.R:57-74) ---------------------------------------
+    def row_stats_csr(self, p, x, n_cells: int):
+        """hs_row_stats_csr: (mean, sd) per CSR row, sd with the n-1 denominator and the implicit zeros
+        counted; two-pass fp64 on the device."""
+        p = np.ascontiguousarray(p)
+        if p.dtype not in (np.int32, np.int64):
+            p = p.astype(np.int64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        m = p.size - 1
+        mean, sd = np.empty(m), np.empty(m)
+        self._check(self._lib.hs_row_stats_csr(self._h, _ptr(p), int(p.dtype == np.int64), _ptr(x), m, int(n_cells),
+                                               _ptr(mean), _ptr(sd)), "hs_row_stats_csr")
+        return mean, sd
+
+    def row_stats_csr_dev(self, p_dev, x_dev, n_cells: int, mean_dev, sd_dev):
+        self._check(self._lib.hs_row_stats_csr_dev(self._h, _dptr(p_dev), _dptr(x_dev), p_dev.numel() - 1, int(n_cells),
+                                                   _dptr(mean_dev), _dptr(sd_dev)), "hs_row_stats_csr_dev")
+
     # -- K1 -----------------------------------------------------------------------------------
     def density(self, x, grid, w_q=None, want_densities=False, want_nearest=False):
         """hs_density: x (N,d), grid (G,d) in the same (scaled) space.  Returns dict with

@@ -158,7 +158,8 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
                    device.perm_sample)
       cv_folds     (folds_for_mean_model, folds_for_sd_model) replacing sample(rep(1:10, ...))
       row_stats    (mean, sd) per gene computed by the caller (the R shim passes R's own
-                   Matrix::rowMeans / rowSds, so the integer gene selection is R's even for tied genes)
+                   Matrix::rowMeans / rowSds, so the integer gene selection is R's even for tied genes);
+                   or "device": sparse input is reduced by hs_row_stats_csr (fp64, two-pass) on the GPU
       ctx/device   an existing DeviceContext, or the CUDA device ordinal to create one on
       return_densities  fill info["densities"] (N x G fp64, 800 MB at 1M cells) as the reference does
     """
@@ -198,7 +199,17 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         if isinstance(expression, _sparse.dgCMatrix) or not isinstance(expression, _sparse.dgRMatrix):
             _message(verbose, "### converting expression data from dgCMatrix to dgRMatrix")
         expression = _sparse.as_RsparseMatrix(expression)
-    if row_stats is not None:
+    own_ctx = False
+    if isinstance(row_stats, str):
+        if row_stats != "device":
+            raise ValueError("row_stats must be a (mean, sd) pair, None or 'device'")
+        if sparse_in:                  # one fp64 two-pass kernel instead of a host pass over the matrix
+            if ctx is None:
+                ctx, own_ctx = DeviceContext(device), True
+            expr_mean, expr_sd = ctx.row_stats_csr(expression.p, expression.x, expression.shape[1])
+        else:
+            expr_mean, expr_sd = row_mean_sd(expression)
+    elif row_stats is not None:
         expr_mean = np.asarray(row_stats[0], dtype=np.float64).copy()
         expr_sd = np.asarray(row_stats[1], dtype=np.float64).copy()
         if expr_mean.shape != (expression.shape[0],) or expr_sd.shape != expr_mean.shape:
@@ -274,9 +285,8 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
             warnings.warn(f"The number of grid points was changed from {grid_points} to {grid_coord.shape[0]}")
             grid_points = grid_coord.shape[0]
 
-    own_ctx = ctx is None
-    if own_ctx:
-        ctx = DeviceContext(device)
+    if ctx is None:
+        ctx, own_ctx = DeviceContext(device), True
     try:
         # ---- K1: density stage on the device (:168-186) -----------------------------------
         dens = ctx.density(x, grid_coord, w_q=weights_advanced_Q, want_densities=return_densities)

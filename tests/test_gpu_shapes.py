@@ -69,3 +69,49 @@ def test_shape_sweep(ctx, n, d, g, m, rho):
     got_d = ctx.dkl_perm_dense(dense[rows[1]], np.asfortranarray(perms.T), index_base=1)
     okd = np.abs(want_d) > 1e-9
     assert _rel(got_d[okd], want_d[okd]) < RTOL and np.max(np.abs(got_d[~okd] - want_d[~okd]), initial=0) < 1e-9
+
+
+def test_row_stats_csr_match_oracle_and_selection(ctx, toy, monkeypatch):
+    """hs_row_stats_csr (R/haystack_continuous.R:57-74): fp64 two-pass mean / sd per CSR row on the device;
+    the integer gene selection computed from them must be the oracle's."""
+    from oracle import haystack_oracle as ho
+    from singlecellhaystack_b200 import haystack as hh
+    sp = ho.RowSparse.from_dense(toy["expression"].astype(np.float64))
+    want_mean, want_sd = ho.row_mean_sd(sp)
+    mean, sd = ctx.row_stats_csr(sp.p, sp.x, sp.shape[1])
+    np.testing.assert_allclose(mean, want_mean, rtol=1e-14, atol=0)
+    np.testing.assert_allclose(sd, want_sd, rtol=1e-13, atol=0)
+    keep = want_sd > 0
+    cv_dev, cv_ref = (sd[keep] + 1e-300) / (mean[keep] + 1e-300), (want_sd[keep] + 1e-300) / (want_mean[keep] + 1e-300)
+    # the selection picks the same coefficient-of-variation ranks (genes with tied CVs -- the toy data has
+    # rows that are permutations of each other -- may swap, in R as well: their order hangs on the last bit)
+    sel_dev = hh.select_genes_to_randomize(cv_dev, 100, "heavytails")
+    sel_ref = ho.select_genes_to_randomize(cv_ref, 100, "heavytails")
+    np.testing.assert_allclose(cv_ref[sel_dev], cv_ref[sel_ref], rtol=1e-12, atol=0)
+    # int32 row pointers, several upload pieces, empty rows and a constant row (sd == 0 exactly)
+    monkeypatch.setenv("HS_STAGE_VALUES", "4096")
+    m2, s2 = ctx.row_stats_csr(sp.p.astype(np.int32), sp.x, sp.shape[1])
+    np.testing.assert_array_equal(m2, mean)
+    np.testing.assert_array_equal(s2, sd)
+    p = np.array([0, 0, 5, 5, 6], dtype=np.int64)
+    x = np.array([2.0, 2.0, 2.0, 2.0, 2.0, 7.5])
+    m3, s3 = ctx.row_stats_csr(p, x, 5)
+    np.testing.assert_array_equal(m3, [0.0, 2.0, 0.0, 1.5])
+    assert s3[0] == 0 and s3[1] == 0 and s3[2] == 0
+    assert abs(s3[3] - np.std([7.5, 0, 0, 0, 0], ddof=1)) < 1e-15
+
+
+def test_front_door_with_device_row_stats(ctx, toy):
+    import warnings
+    from oracle import haystack_oracle as ho
+    from singlecellhaystack_b200 import haystack as hh, sparse as sp_, synth
+    seed = int(toy["seed"])
+    folds = (synth.cv_folds(seed, 0, 100), synth.cv_folds(seed, 1, 100))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = hh.haystack(toy["coord"], sp_.as_CsparseMatrix(toy["expression"].astype(np.float64)), grid_coord=toy["grid100"],
+                          perm_source=synth.perm_source(seed), row_stats="device", cv_folds=folds, ctx=ctx, verbose=False)
+    assert np.max(np.abs(res["results"]["D_KL"].values - toy["dkl100"]) / toy["dkl100"]) < RTOL
+    same = np.array_equal(res["info"]["randomization"]["genes_to_randomize"], toy["full_genes_to_randomize"] + 1)
+    # identical selection -> identical null sample -> identical p-values; tied genes swapped -> another null sample
+    assert np.max(np.abs(res["results"]["log.p.vals"].values - toy["full_log_p"])) < (1e-3 if same else 1.5)
