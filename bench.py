@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--perm-draw", default="device", choices=["device", "host"],
                     help="randomization draw sample(n_cells, nnz) (R/haystack_continuous.R:275): made on the device "
                          "from a seed (hs_dkl_perm_csr_seeded, default) or passed in as ids (hs_dkl_perm_csr)")
+    ap.add_argument("--e2e-separate-calls", action="store_true",
+                    help="e2e: hs_dkl_csr then hs_dkl_perm_csr_seeded instead of the single hs_dkl_csr_randomized call")
     ap.add_argument("--no-dense", action="store_true", help="skip the side measurement of the dense (tcgen05) kernel")
     ap.add_argument("--dense-genes", type=int, default=1024)
     ap.add_argument("--cpu-genes", type=int, default=24)
@@ -376,6 +378,7 @@ def run_b200(a):
         gene_ptr, pval, pind, r_loc = make_perm_inputs_device(a, p_host, vals, sel_local, sel, 0, a.rand_count, dev,
                                                               want_ids=a.perm_draw == "host")
         mine = np.arange(len(sel))
+        a._sel_rows = sel_local
     else:
         # units = (selected gene, block of permutations), dealt to ranks by descending cost (LPT) so that the
         # fixed total of S x R permuted rows is balanced; the selected rows' values are exchanged once
@@ -639,6 +642,11 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
         pi_h.copy_(pind)
     pv64 = pv_h.numpy().astype(np.float64) if seeded else None     # the seeded entry point takes doubles
     perm_stream_base = rank << 40
+    # one call for the observed scores and the seeded randomization batch (the batch computes while the matrix
+    # uploads) when the selected rows are rows of this rank's matrix
+    sel_rows = getattr(a, "_sel_rows", None)
+    combined = (seeded and world == 1 and value_dtype == "float64" and sel_rows is not None and n_sel_local
+                and int(np.max(sel_rows)) < m_e2e and not a.e2e_separate_calls)
     xs_h = torch.from_numpy(np.ascontiguousarray(xs.T)).pin_memory()       # column-major N x d
     grid_h = torch.from_numpy(np.ascontiguousarray(grid.T)).pin_memory()
     torch.cuda.synchronize()
@@ -651,6 +659,10 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
             ctx.density(xs_h.numpy().T, grid_h.numpy().T)
         if world > 1:
             ctx.density_broadcast(a.cells, a.grid_points, src=0)
+        if combined:
+            d, _ = ctx.dkl_csr_randomized(p_np, j_np, x_np, sel_rows, r_loc, PERM_SEED, stream_base=perm_stream_base,
+                                          out_rand=out_rand)
+            return d
         d = ctx.dkl_csr(p_np, j_np, x_np)
         if n_sel_local:
             if seeded:
@@ -680,7 +692,8 @@ def run_e2e(a, ctx, xs, grid, p, cols, vals, gene_ptr, pval, pind, r_loc, n_sel_
             "ms_per_step": per * 1e3, "steps": a.e2e_steps, "genes_per_gpu": m_e2e,
             "host_value_bytes": 8 if value_dtype == "float64" else 4, "pcie_value_bytes": int(vbytes),
             "perm_draw": a.perm_draw,
-            "note": (f"hs_density + hs_dkl_csr + {'hs_dkl_perm_csr_seeded' if seeded else 'hs_dkl_perm_csr'} with pinned host "
+            "note": (f"hs_density + " + ("hs_dkl_csr_randomized" if combined else
+                                         f"hs_dkl_csr + {'hs_dkl_perm_csr_seeded' if seeded else 'hs_dkl_perm_csr'}") + " with pinned host "
                      f"buffers ({value_dtype} values, int32 ids), "
                      "timed with the host clock around the blocking calls"
                      + ("" if m_e2e == m else f"; host memory limits the e2e pass to the first {m_e2e} genes"))}

@@ -140,6 +140,14 @@ int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, 
  * n_cells x n_perm index matrix.  hs_perm_sample(seed, stream_base + r, n_cells, n_cells, ...) returns pi_r. */
 int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t seed, uint64_t stream_base,
                              double* out);
+/* hs_dkl_csr and hs_dkl_perm_csr_seeded for the rows sel_rows[0..n_sel) (0-based row numbers of the same
+ * matrix, in the order of genes.to.randomize) in one call: the randomization batch is launched first and
+ * computes while the matrix is still being uploaded.  Results are bit-identical to the two separate calls
+ * (R/haystack_continuous.R:199-213 and :245-284; the selection :222-236 needs only the row statistics, so it
+ * can precede both).  rand_out: n_sel x n_perm column-major. */
+int hs_dkl_csr_randomized(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x,
+                          int64_t n_genes, const int64_t* sel_rows, int64_t n_sel, int n_perm,
+                          uint64_t seed, uint64_t stream_base, double* dkl_out, double* rand_out);
 /* Host helper (no GPU involved): ids_out[i] = pi(i) + index_base for i < size, pi keyed by
  * (seed, stream) over [0, n).  1 <= n < 2^31, 0 <= size <= n. */
 int hs_perm_sample(uint64_t seed, uint64_t stream, int64_t n, int64_t size, int index_base,

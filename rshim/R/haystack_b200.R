@@ -82,3 +82,14 @@ b200_randomize <- function(dev, expression, genes.to.randomize, randomization.co
 
 b200_perm_sample <- function(seed, stream, n, size)
   .Call("hsb_perm_sample", as.double(seed), as.double(stream), as.double(n), as.double(size), PACKAGE = "haystackB200")
+
+# D_KL of every gene and the seeded randomization of genes.to.randomize in one call (the randomization batch
+# computes while the matrix uploads): replaces :199-213 and :245-284 once genes.to.randomize (:222-236) is known
+b200_dkl_csr_randomized <- function(dev, expression, genes.to.randomize, randomization.count,
+                                    seed = sample.int(.Machine$integer.max, 1)) {
+  res <- .Call("hsb_dkl_csr_randomized", dev, expression@p, expression@j, expression@x,
+               as.integer(genes.to.randomize), as.integer(randomization.count), as.double(seed),
+               PACKAGE = "haystackB200")
+  names(res) <- c("D_KL", "all.D_KL.randomized")
+  res
+}

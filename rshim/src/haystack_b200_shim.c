@@ -134,6 +134,25 @@ SEXP hsb_dkl_perm_dense_seeded(SEXP sctx, SEXP v, SEXP n_perm, SEXP seed, SEXP s
   return out;
 }
 
+/* Scores of all genes and the seeded randomization of rows sel (1-based, order of genes.to.randomize) in one
+ * call; returns list(D_KL, all.D_KL.randomized). */
+SEXP hsb_dkl_csr_randomized(SEXP sctx, SEXP p, SEXP j, SEXP x, SEXP sel, SEXP n_perm, SEXP seed) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t m = XLENGTH(p) - 1, s = XLENGTH(sel);
+  const int r = asInteger(n_perm);
+  int64_t* rows = (int64_t*)R_alloc((size_t)s + 1, sizeof(int64_t));
+  for (int64_t i = 0; i < s; ++i) rows[i] = (int64_t)INTEGER(sel)[i] - 1;
+  SEXP dkl = PROTECT(allocVector(REALSXP, (R_xlen_t)m));
+  SEXP rnd = PROTECT(allocMatrix(REALSXP, (int)s, r));
+  check(ctx, hs_dkl_csr_randomized(ctx, INTEGER(p), 0, INTEGER(j), REAL(x), m, rows, s, r, (uint64_t)asReal(seed), 0,
+                                   REAL(dkl), REAL(rnd)), "hs_dkl_csr_randomized");
+  SEXP out = PROTECT(allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, dkl);
+  SET_VECTOR_ELT(out, 1, rnd);
+  UNPROTECT(3);
+  return out;
+}
+
 /* ids of one draw (1-based), for reproducing a seeded randomization in R */
 SEXP hsb_perm_sample(SEXP seed, SEXP stream, SEXP n, SEXP size) {
   const int64_t k = (int64_t)asReal(size);
@@ -155,6 +174,7 @@ static const R_CallMethodDef call_methods[] = {
     {"hsb_dkl_perm_csr", (DL_FUNC)&hsb_dkl_perm_csr, 5},
     {"hsb_dkl_perm_csr_seeded", (DL_FUNC)&hsb_dkl_perm_csr_seeded, 5},
     {"hsb_dkl_perm_dense_seeded", (DL_FUNC)&hsb_dkl_perm_dense_seeded, 5},
+    {"hsb_dkl_csr_randomized", (DL_FUNC)&hsb_dkl_csr_randomized, 7},
     {"hsb_perm_sample", (DL_FUNC)&hsb_perm_sample, 4},
     {NULL, NULL, 0}};
 

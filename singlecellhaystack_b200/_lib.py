@@ -40,6 +40,7 @@ SIGNATURES = {
     "hs_dkl_perm_csr_seeded": (_int, [_vp, _vp, _i64, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
     "hs_dkl_perm_dense_seeded": (_int, [_vp, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
     "hs_dkl_perm_dense_seeded_dev": (_int, [_vp, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
+    "hs_dkl_csr_randomized": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp, _i64, _int, C.c_uint64, C.c_uint64, _vp, _vp]),
     "hs_perm_sample": (_int, [C.c_uint64, C.c_uint64, _i64, _i64, _int, _vp]),
     "hs_dkl_csr_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "hs_dkl_perm_csr_seeded_dev": (_int, [_vp, _vp, _i64, _vp, _int, C.c_uint64, C.c_uint64, _vp]),

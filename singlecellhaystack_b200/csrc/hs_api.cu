@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -262,7 +263,7 @@ void hs_destroy(hs_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->D32, &ctx->Q, &ctx->sq, &ctx->rowmin, &ctx->nearest, &ctx->sel, &ctx->qpart,
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
-                    &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals};
+                    &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals, &ctx->perm_gp, &ctx->out_rand};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int k = 0; k < hs_ctx::kRing; ++k) {
@@ -459,10 +460,14 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   // row pointers rebased to the uploaded arrays
   std::vector<int64_t> rel((size_t)n_units + 1);
   for (int64_t u = 0; u <= n_units; ++u) rel[u] = hp[u] - v0;
-  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, rel.data(), sizeof(int64_t) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, st));
   // the copy stream must not overtake work of earlier calls that still reads the buffers
-  HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
-  HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));
+  if (!ctx->skip_copy_fence) {
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
+    HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));
+  }
+  // (on the copy stream: a pageable source makes this call wait for the copy, which on the compute stream
+  // would queue behind whatever is running there; every piece's event covers it)
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, rel.data(), sizeof(int64_t) * (size_t)(n_units + 1), cudaMemcpyHostToDevice, cs));
 
   // Uploads (and the fp64 -> fp32 conversion of the values) run on the copy stream; the contraction of a
   // piece of rows starts on the compute stream as soon as that piece has landed, so PCIe transfer and
@@ -598,6 +603,78 @@ static int dkl_csr_any(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j
 int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
                double* dkl_out) {
   return dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out);
+}
+
+// Observed D_KL of every gene and the seeded randomization batch of the selected ones in ONE call: the
+// batch (values of ~100 rows, a few MB) is uploaded and launched first and computes while the CSR matrix
+// is still crossing PCIe, instead of after it (hs_dkl_csr followed by hs_dkl_perm_csr_seeded).
+int hs_dkl_csr_randomized(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
+                          const int64_t* sel_rows, int64_t n_sel, int n_perm, uint64_t seed, uint64_t stream_base,
+                          double* dkl_out, double* rand_out) {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || n_sel < 0 || n_perm <= 0 || !p || !dkl_out || (n_sel > 0 && (!sel_rows || !rand_out)))
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr_randomized: bad arguments");
+  auto ptr_at = [&](int64_t i) { return p_is_64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i]; };
+  std::vector<int64_t> gp((size_t)n_sel + 1, 0);
+  for (int64_t s = 0; s < n_sel; ++s) {
+    const int64_t r = sel_rows[s];
+    if (r < 0 || r >= n_genes) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr_randomized: selected row out of range");
+    const int64_t nnz = ptr_at(r + 1) - ptr_at(r);
+    if (nnz < 0 || nnz > ctx->N) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr_randomized: bad row length");
+    gp[(size_t)s + 1] = gp[(size_t)s] + nnz;
+  }
+  const int64_t nv = gp[(size_t)n_sel];
+  if (nv > 0 && !x) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr_randomized: x is NULL");
+  size_t free_b = 0, total_b = 0;
+  HS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  free_b += ctx->perm_cols.cap;
+  const bool fits = (double)nv * (8.0 * n_perm + 16.0) < 0.25 * (double)free_b;   // leave the CSR upload its room
+  if (n_sel > 0 && fits) {
+    cudaStream_t st = ctx->stream;
+    std::unique_ptr<float[]> v32(new float[(size_t)hs_max<int64_t>(nv, 1)]);
+    {
+      float* base = v32.get();
+      auto rows = [&, base](int t, int nt) {
+        for (int64_t s = t; s < n_sel; s += nt) {
+          const double* src = x + ptr_at(sel_rows[s]);
+          float* dst = base + gp[(size_t)s];
+          const int64_t n = gp[(size_t)s + 1] - gp[(size_t)s];
+          for (int64_t i = 0; i < n; ++i) dst[i] = (float)src[i];
+        }
+      };
+      if (nv < ((int64_t)1 << 18) || host_threads() == 1) {
+        rows(0, 1);
+      } else {
+        if (!ctx->pool) ctx->pool = new HostPool(host_threads());
+        const int nt = ctx->pool->size();
+        ctx->pool->run([&](int t) { rows(t, nt); });
+      }
+    }
+    HS_TRY(hs_ensure(ctx, ctx->perm_gp, sizeof(int64_t) * (size_t)(n_sel + 1)));
+    HS_TRY(hs_ensure(ctx, ctx->perm_vals, sizeof(float) * (size_t)hs_max<int64_t>(nv, 1)));
+    HS_TRY(hs_ensure(ctx, ctx->out_rand, sizeof(double) * (size_t)(n_sel * n_perm)));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->perm_gp.p, gp.data(), sizeof(int64_t) * (size_t)(n_sel + 1), cudaMemcpyHostToDevice, st));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->perm_vals.p, v32.get(), sizeof(float) * (size_t)nv, cudaMemcpyHostToDevice, st));
+    HS_CUDA(ctx, cudaStreamSynchronize(st));     // pageable sources; nothing else is queued yet
+    HS_TRY(hs_run_perm_seeded(ctx, (const int64_t*)ctx->perm_gp.p, n_sel, nv, (const float*)ctx->perm_vals.p, n_perm, seed,
+                              stream_base, (double*)ctx->out_rand.p));
+    // the batch reads none of the CSR upload buffers: the uploads need not wait for it
+    ctx->skip_copy_fence = true;
+    const int rc = dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out);
+    ctx->skip_copy_fence = false;
+    HS_TRY(rc);
+    HS_CUDA(ctx, cudaMemcpyAsync(rand_out, ctx->out_rand.p, sizeof(double) * (size_t)(n_sel * n_perm), cudaMemcpyDeviceToHost, st));
+    HS_CUDA(ctx, cudaStreamSynchronize(st));
+    return HS_OK;
+  }
+  // randomization batch too large to sit beside the upload: one after the other
+  HS_TRY(dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out));
+  if (n_sel == 0) return HS_OK;
+  std::vector<double> vsel((size_t)hs_max<int64_t>(nv, 1));
+  for (int64_t s = 0; s < n_sel; ++s)
+    memcpy(vsel.data() + gp[(size_t)s], x + ptr_at(sel_rows[s]), sizeof(double) * (size_t)(gp[(size_t)s + 1] - gp[(size_t)s]));
+  return hs_dkl_perm_csr_seeded(ctx, gp.data(), n_sel, vsel.data(), n_perm, seed, stream_base, rand_out);
 }
 
 int hs_dkl_csr_f32(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const float* x, int64_t n_genes,

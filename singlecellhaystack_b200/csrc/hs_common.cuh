@@ -71,7 +71,9 @@ struct hs_ctx {
   bool tiles_valid = false;    // the tiles match the resident density matrix
   DevBuf umma_flags;
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
-  DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, slab-bucketed (id, value) pairs
+  DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, (id, value) pairs, values of the selected rows
+  DevBuf perm_gp, out_rand;               // hs_dkl_csr_randomized: gene pointers and results of the randomization batch
+  bool skip_copy_fence = false;           // the caller guarantees that nothing in flight reads the upload buffers
   void* pinned = nullptr;      // small pinned host bounce buffer
   size_t pinned_cap = 0;
   // host-side fp64 -> fp32 narrowing of uploaded values (hs_api.cu): pinned ring + worker threads

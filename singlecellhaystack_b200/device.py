@@ -307,6 +307,25 @@ class DeviceContext:
                     "hs_dkl_perm_csr_seeded")
         return out
 
+    def dkl_csr_randomized(self, p, j, x, sel_rows, n_perm: int, seed: int, stream_base: int = 0, out_rand=None):
+        """hs_dkl_csr_randomized: D_KL of every CSR row plus the seeded randomization batch of rows `sel_rows`
+        (0-based) in one call; the batch computes while the matrix uploads.  Returns (dkl (M,), rand (S, R))."""
+        p = np.ascontiguousarray(p)
+        if p.dtype not in (np.int32, np.int64):
+            p = p.astype(np.int64)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        sel = np.ascontiguousarray(sel_rows, dtype=np.int64)
+        m = p.size - 1
+        dkl = np.empty(m, dtype=np.float64)
+        if out_rand is None:
+            out_rand = np.empty((sel.size, int(n_perm)), dtype=np.float64, order="F")
+        self._check(self._lib.hs_dkl_csr_randomized(self._h, _ptr(p), int(p.dtype == np.int64), _ptr(j), _ptr(x), m,
+                                                    _ptr(sel), sel.size, int(n_perm), int(seed) % (1 << 64),
+                                                    int(stream_base) % (1 << 64), _ptr(dkl), _ptr(out_rand)),
+                    "hs_dkl_csr_randomized")
+        return dkl, out_rand
+
     def dkl_perm_csr_seeded_flat(self, gene_ptr, val, n_perm, seed, stream_base=0, out=None) -> np.ndarray:
         """hs_dkl_perm_csr_seeded on flattened host arrays (gene_ptr int64 [S+1], val fp64)."""
         gene_ptr = np.ascontiguousarray(gene_ptr, dtype=np.int64)

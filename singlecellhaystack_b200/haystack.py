@@ -293,13 +293,9 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
 
         # ---- K2 / K3: observed D_KL (:199-213) --------------------------------------------
         _message(verbose, "### calculating Kullback-Leibler divergences...")
-        if sparse_in:
-            D_KL_observed = ctx.dkl_csr(expression.p, expression.j, expression.x)
-        else:
-            D_KL_observed = ctx.dkl_dense(expression)
-
+        # The gene selection (:222-236) needs only the row statistics, so it can precede the scoring; that lets
+        # the sparse path with device draws score the genes and the randomization batch in one call.
         coeffVar = expr_sd / expr_mean                                                   # :222
-        _message(verbose, "### performing randomizations...")
         genes_to_randomize = select_genes_to_randomize(coeffVar, n_genes_to_randomize,
                                                        selection_method_genes_to_randomize)
         info_perm_seed = None
@@ -307,14 +303,25 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         if device_draw and perm_source != "device":
             raise ValueError("perm_source must be a callable, None or 'device'")
         src = None if device_draw else (perm_source if perm_source is not None else _NumpyPermSource(rng))
-
-        # ---- K4: randomized D_KL (:245-284); draws in the reference's order (gene-major) ---
         all_D_KL_randomized = np.full((n_genes_to_randomize, randomization_count), np.nan)
+
         if sparse_in and device_draw:
             perm_seed = int(rng.integers(0, 2 ** 63))
-            vals = [_sparse.extract_row_dgRMatrix_as_sparse(expression, int(g) + 1)["val"] for g in genes_to_randomize]
-            all_D_KL_randomized[:, :] = ctx.dkl_perm_csr_seeded(vals, randomization_count, perm_seed)
+            _message(verbose, "### performing randomizations...")
+            D_KL_observed, rand = ctx.dkl_csr_randomized(expression.p, expression.j, expression.x, genes_to_randomize,
+                                                         randomization_count, perm_seed)
+            all_D_KL_randomized[:, :] = rand
             info_perm_seed = perm_seed
+        elif sparse_in:
+            D_KL_observed = ctx.dkl_csr(expression.p, expression.j, expression.x)
+        else:
+            D_KL_observed = ctx.dkl_dense(expression)
+        if not (sparse_in and device_draw):
+            _message(verbose, "### performing randomizations...")
+
+        # ---- K4: randomized D_KL (:245-284); draws in the reference's order (gene-major) ---
+        if sparse_in and device_draw:
+            pass
         elif sparse_in:
             budget = 64 << 20          # ids per device call
             batch_vals, batch_inds, batch_rows, used = [], [], [], 0

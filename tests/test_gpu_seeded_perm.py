@@ -156,3 +156,24 @@ def test_dense_front_door_with_device_draws(ctx, toy):
     perms = np.stack([po.prp_sample(ps, 3 * 25 + r, 601, 601) for r in range(25)])
     want = ho.dkl_randomized_dense(expr[[g0]], perms[None], ref["density"], ref["Q"])[0]
     assert _rel(rnd["KLD_rand"][3], want) < RTOL_DKL
+
+
+def test_combined_call_equals_separate_calls(ctx, toy):
+    """hs_dkl_csr_randomized launches the randomization batch before the matrix upload; scores and randomized
+    scores must be bit-identical to hs_dkl_csr followed by hs_dkl_perm_csr_seeded."""
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ctx.density(xs, toy["grid100"])
+    sp = ho.RowSparse.from_dense(toy["expression"])
+    sel = toy["full_genes_to_randomize"][:15].astype(np.int64)
+    dkl, rnd = ctx.dkl_csr_randomized(sp.p, sp.j, sp.x, sel, 12, 31337, stream_base=7)
+    np.testing.assert_array_equal(dkl, ctx.dkl_csr(sp.p, sp.j, sp.x))
+    vals = [sp.x[sp.p[g]:sp.p[g + 1]] for g in sel]
+    np.testing.assert_array_equal(rnd, ctx.dkl_perm_csr_seeded(vals, 12, 31337, stream_base=7))
+    assert _rel(dkl, toy["dkl100"]) < RTOL_DKL
+    # no selected rows: plain scoring
+    dkl0, rnd0 = ctx.dkl_csr_randomized(sp.p, sp.j, sp.x, np.zeros(0, dtype=np.int64), 5, 1)
+    np.testing.assert_array_equal(dkl0, dkl)
+    assert rnd0.shape == (0, 5)
+    from singlecellhaystack_b200.device import HaystackLibraryError
+    with pytest.raises(HaystackLibraryError, match="out of range"):
+        ctx.dkl_csr_randomized(sp.p, sp.j, sp.x, np.array([500], dtype=np.int64), 5, 1)
