@@ -14,8 +14,12 @@ it fits one B200 (24 GB of CSR).  With N > 1 every rank holds its own 30k-gene s
 every rank scores its slice and its share of the (gene, permutation-block) units, and D_KL is
 all-gathered.
 
+The draws of K4, sample(x = n_cells, size = nnz) (:275), are made on the device from a seed by default
+(hs_dkl_perm_csr_seeded; --perm-draw host passes pre-drawn ids through hs_dkl_perm_csr instead).
+
 `value` is measured with every input resident in HBM; `e2e` goes through the host-pointer C ABI
-(hs_density / hs_dkl_csr / hs_dkl_perm_csr) with the inputs in pinned host memory.  The
+(hs_density + hs_dkl_csr_randomized at N=1, hs_dkl_csr + hs_dkl_perm_csr_seeded per rank at N>1) with the
+inputs in pinned host memory holding R's types (fp64 values, int32 ids).  The
 `cpu_baseline` object and `--impl reference` time the fp64 oracle (a restatement of the R code;
 R itself exists neither here nor on the GPU box) on the box's host cores.
 """
