@@ -80,6 +80,8 @@ def haystack_continuous_highD_sharded(x, expression, backend, grid_coord, *, gro
     """Gene-sharded haystack_continuous_highD (R/haystack_continuous.R:27-339) with a supplied grid.
 
     backend: this rank's DeviceContext (or an object with the same compute methods).
+    perm_source: callable / None as in haystack_continuous_highD, or "device": the draws are made by the
+    backend from `seed` (hs_dkl_perm_csr_seeded / hs_dkl_perm_dense_seeded).
     Returns the same Haystack object on every rank."""
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -138,11 +140,26 @@ def haystack_continuous_highD_sharded(x, expression, backend, grid_coord, *, gro
 
     coeff_var = expr_sd / expr_mean
     genes = _hs.select_genes_to_randomize(coeff_var, n_sel, selection_method_genes_to_randomize)
-    src = perm_source if perm_source is not None else _GeneStreams(seed)
+    device_draw = isinstance(perm_source, str)
+    if device_draw and perm_source != "device":
+        raise ValueError("perm_source must be a callable, None or 'device'")
+    src = None if device_draw else (perm_source if perm_source is not None else _GeneStreams(seed))
     owners = owner_of(genes, bounds)
     mine = np.nonzero(owners == rank)[0]
     rows_local = np.zeros((mine.size, randomization_count))
-    if mine.size:
+    if mine.size and device_draw:
+        # draws made on the device; the stream of (gene, r) is its position in `genes` * R + r, whoever owns
+        # the gene, so the result does not depend on the number of ranks
+        for k, i in enumerate(mine):
+            base = int(i) * int(randomization_count)
+            if sparse_in:
+                row = _sparse.extract_row_dgRMatrix_as_sparse(expression, int(genes[i]) + 1)
+                rows_local[k] = np.asarray(backend.dkl_perm_csr_seeded([row["val"]], randomization_count, seed,
+                                                                       stream_base=base))[0]
+            else:
+                rows_local[k] = backend.dkl_perm_dense_seeded(expression[int(genes[i])], randomization_count, seed,
+                                                              stream_base=base)
+    elif mine.size:
         if sparse_in:
             vals, inds = [], []
             for i in mine:

@@ -60,6 +60,19 @@ class _OracleBackend:
         from oracle import haystack_oracle as ho
         return ho.dkl_randomized_sparse(vals, [np.asarray(a).T for a in inds], self.state["density"], self.state["Q"])
 
+    def dkl_perm_csr_seeded(self, vals, n_perm, seed, stream_base=0):
+        from oracle import haystack_oracle as ho, prp_oracle as po
+        n = self.state["density"].shape[0]
+        inds = [np.stack([po.prp_sample(seed, stream_base + s * n_perm + r, n, len(v)) for r in range(n_perm)])
+                for s, v in enumerate(vals)]
+        return ho.dkl_randomized_sparse(vals, inds, self.state["density"], self.state["Q"])
+
+    def dkl_perm_dense_seeded(self, v, n_perm, seed, stream_base=0):
+        from oracle import haystack_oracle as ho, prp_oracle as po
+        n = self.state["density"].shape[0]
+        perms = np.stack([po.prp_sample(seed, stream_base + r, n, n) for r in range(n_perm)])
+        return ho.dkl_randomized_dense(np.asarray(v)[None], perms[None], self.state["density"], self.state["Q"])[0]
+
     def dkl_perm_dense(self, v, perm, index_base=1):
         from oracle import haystack_oracle as ho
         return ho.dkl_randomized_dense(np.asarray(v)[None], np.asarray(perm).T[None], self.state["density"], self.state["Q"])[0]
@@ -109,3 +122,50 @@ def test_two_rank_gloo_matches_single_process_golden(toy, form):
     gold_logp = toy["full_log_p"] if form == "sparse" else toy["fulld_log_p"]
     np.testing.assert_allclose(kr0, gold_rand, rtol=1e-12)
     assert np.max(np.abs(lp0 - gold_logp)) < 1e-6
+
+
+def _worker_device_draw(rank, world, port, out):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    from singlecellhaystack_b200 import sparse as sp
+    from singlecellhaystack_b200 import synth
+    from singlecellhaystack_b200.distributed import haystack_continuous_highD_sharded
+    from oracle import haystack_oracle as ho
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        toy = np.load(ROOT / "tests" / "golden" / "toy.npz")
+        seed = int(toy["seed"])
+        expr = toy["expression"].astype(np.float64)
+        stats = ho.row_mean_sd(ho.RowSparse.from_dense(expr))
+        res = haystack_continuous_highD_sharded(
+            toy["coord"], sp.as_CsparseMatrix(expr), _OracleBackend(), toy["grid100"], perm_source="device", seed=4711,
+            row_stats=stats, n_genes_to_randomize=30, randomization_count=20,
+            cv_folds=(synth.cv_folds(seed, 0, 30), synth.cv_folds(seed, 1, 30)))
+        out[rank] = (res["info"]["randomization"]["KLD_rand"].copy(), res["results"]["log.p.vals"].values.copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_device_draws_do_not_depend_on_world_size(toy):
+    """perm_source="device": the stream of a (gene, randomization) pair is fixed by its position in the
+    selection, so two ranks reproduce the single-process result exactly."""
+    import torch.multiprocessing as mp
+    from oracle import haystack_oracle as ho
+    from singlecellhaystack_b200 import sparse as sp
+    from singlecellhaystack_b200 import synth
+    from singlecellhaystack_b200.distributed import haystack_continuous_highD_sharded
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(_worker_device_draw, args=(2, port, out), nprocs=2, join=True)
+    seed = int(toy["seed"])
+    expr = toy["expression"]
+    single = haystack_continuous_highD_sharded(
+        toy["coord"], sp.as_CsparseMatrix(expr), _OracleBackend(), toy["grid100"], perm_source="device", seed=4711,
+        row_stats=ho.row_mean_sd(ho.RowSparse.from_dense(expr)), n_genes_to_randomize=30, randomization_count=20,
+        cv_folds=(synth.cv_folds(seed, 0, 30), synth.cv_folds(seed, 1, 30)))
+    np.testing.assert_array_equal(out[0][0], out[1][0])
+    np.testing.assert_array_equal(out[0][0], single["info"]["randomization"]["KLD_rand"])
+    np.testing.assert_allclose(out[0][1], single["results"]["log.p.vals"].values, rtol=0, atol=1e-12)
