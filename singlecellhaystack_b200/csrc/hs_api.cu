@@ -19,7 +19,14 @@
 
 static thread_local std::string g_global_err;
 
+// No C++ exception may cross the C ABI (host allocations of the staging code can throw).
+#define HS_ABI_CATCH(ctxp)                                                                       \
+  catch (const std::bad_alloc&) { return hs_fail((ctxp), HS_ERR_NOMEM, "host allocation failed"); } \
+  catch (const std::exception& e) { return hs_fail((ctxp), HS_ERR_INVALID, "internal error: %s", e.what()); } \
+  catch (...) { return hs_fail((ctxp), HS_ERR_INVALID, "internal error"); }
+
 int hs_fail(hs_ctx* ctx, int code, const char* fmt, ...) {
+  try {
   char buf[1024];
   va_list ap;
   va_start(ap, fmt);
@@ -30,9 +37,11 @@ int hs_fail(hs_ctx* ctx, int code, const char* fmt, ...) {
   else
     g_global_err = buf;
   return code;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes) {
+  try {
   if (bytes == 0) bytes = 16;
   if (b.cap >= bytes) return HS_OK;
   if (b.p) {
@@ -58,6 +67,7 @@ int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes) {
     b.cap = want;
   }
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 // ---- host worker threads ---------------------------------------------------------------------------
@@ -283,33 +293,41 @@ void hs_destroy(hs_ctx* ctx) {
 }
 
 int hs_set_stream(hs_ctx* ctx, void* cuda_stream) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   HS_TRY(set_device(ctx));
   HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_synchronize(hs_ctx* ctx) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   HS_TRY(set_device(ctx));
   HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int64_t hs_launch_count(const hs_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int hs_enable_timers(hs_ctx* ctx, int on) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   ctx->timers = on != 0;
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_last_timers(hs_ctx* ctx, float* ms_out, int n_slots) {
+  try {
   if (!ctx || !ms_out) return 0;
   const int n = std::min(n_slots, (int)HS_T_COUNT);
   for (int i = 0; i < n; ++i) ms_out[i] = ctx->t_ms[i];
   return n;
+  } HS_ABI_CATCH(ctx)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -349,6 +367,7 @@ static int check_density_args(hs_ctx* ctx, const void* x, int64_t N, int d, cons
 int hs_density(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims, const double* grid, int n_grid,
                const double* w_q, double* bandwidth_out, double* q_out, double* density_out,
                int32_t* nearest_out) {
+  try {
   HS_TRY(check_density_args(ctx, x, n_cells, n_dims, grid, n_grid));
   HS_TRY(set_device(ctx));
   ctx->N = 0;  // state is invalid until the stage completes
@@ -365,26 +384,32 @@ int hs_density(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims, const 
   }
   return density_common(ctx, (const double*)ctx->xin.p, n_cells, n_dims, (const double*)ctx->gin.p, n_grid, w_dev,
                         bandwidth_out, q_out, density_out, nearest_out);
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_density_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims, const double* grid_dev,
                    int n_grid, const double* w_q_dev, double* bandwidth_out, double* q_out) {
+  try {
   HS_TRY(check_density_args(ctx, x_dev, n_cells, n_dims, grid_dev, n_grid));
   HS_TRY(set_device(ctx));
   ctx->N = 0;
   return density_common(ctx, x_dev, n_cells, n_dims, grid_dev, n_grid, w_q_dev, bandwidth_out, q_out, nullptr,
                         nullptr);
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_density_shape(const hs_ctx* ctx, int64_t* n_cells_out, int* n_grid_out) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   if (n_cells_out) *n_cells_out = ctx->N;
   if (n_grid_out) *n_grid_out = ctx->N > 0 ? ctx->G : 0;
   return HS_OK;
+  } HS_ABI_CATCH(nullptr)
 }
 
 int hs_density_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, void** d_dev, int64_t* d_bytes, void** q_dev,
                        int64_t* q_bytes) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   if (n_cells <= 0 || n_grid <= 0 || n_grid > 1024 || n_cells > 2147483647LL || !d_dev || !q_dev)
     return hs_fail(ctx, HS_ERR_INVALID, "hs_density_buffers: bad arguments");
@@ -400,9 +425,11 @@ int hs_density_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, void** d_dev, i
   if (d_bytes) *d_bytes = (int64_t)sizeof(float) * n_cells * ldD;
   if (q_bytes) *q_bytes = (int64_t)sizeof(double) * (n_grid + 1);
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   HS_TRY(set_device(ctx));
   if (n_cells <= 0 || n_grid <= 0 || !ctx->D32.p || !ctx->Q.p)
@@ -424,6 +451,7 @@ int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid) {
   ctx->bw = bw;
   ctx->tiles_valid = false;
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -602,7 +630,9 @@ static int dkl_csr_any(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j
 
 int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
                double* dkl_out) {
+  try {
   return dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out);
+  } HS_ABI_CATCH(ctx)
 }
 
 // Observed D_KL of every gene and the seeded randomization batch of the selected ones in ONE call: the
@@ -611,6 +641,7 @@ int hs_dkl_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const 
 int hs_dkl_csr_randomized(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
                           const int64_t* sel_rows, int64_t n_sel, int n_perm, uint64_t seed, uint64_t stream_base,
                           double* dkl_out, double* rand_out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || n_sel < 0 || n_perm <= 0 || !p || !dkl_out || (n_sel > 0 && (!sel_rows || !rand_out)))
@@ -675,11 +706,14 @@ int hs_dkl_csr_randomized(hs_ctx* ctx, const void* p, int p_is_64, const int32_t
   for (int64_t s = 0; s < n_sel; ++s)
     memcpy(vsel.data() + gp[(size_t)s], x + ptr_at(sel_rows[s]), sizeof(double) * (size_t)(gp[(size_t)s + 1] - gp[(size_t)s]));
   return hs_dkl_perm_csr_seeded(ctx, gp.data(), n_sel, vsel.data(), n_perm, seed, stream_base, rand_out);
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_csr_f32(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const float* x, int64_t n_genes,
                    double* dkl_out) {
+  try {
   return dkl_csr_any(ctx, p, p_is_64, j, x, true, n_genes, dkl_out);
+  } HS_ABI_CATCH(ctx)
 }
 
 static int dkl_perm_csr_any(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const void* val, bool val_f32,
@@ -699,15 +733,20 @@ static int dkl_perm_csr_any(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel,
 
 int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, const int32_t* ind,
                     int n_perm, int index_base, double* out) {
+  try {
   return dkl_perm_csr_any(ctx, gene_ptr, n_sel, val, false, ind, n_perm, index_base, out);
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_csr_f32(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const float* val, const int32_t* ind,
                         int n_perm, int index_base, double* out) {
+  try {
   return dkl_perm_csr_any(ctx, gene_ptr, n_sel, val, true, ind, n_perm, index_base, out);
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* dkl_out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || ld < n_genes || !dkl_out || (n_genes > 0 && !expr))
@@ -741,9 +780,11 @@ int hs_dkl_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, d
   HS_CUDA(ctx, cudaMemcpyAsync(dkl_out, ctx->out.p, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
   HS_CUDA(ctx, cudaStreamSynchronize(st));
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_perm, int index_base, double* out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (!v || !perm || !out || n_perm <= 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense: bad arguments");
@@ -764,6 +805,7 @@ int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_p
   HS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, sizeof(double) * (size_t)n_perm, cudaMemcpyDeviceToHost, st));
   HS_CUDA(ctx, cudaStreamSynchronize(st));
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -771,6 +813,7 @@ int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_p
 // ------------------------------------------------------------------------------------------------
 int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev, int64_t n_genes,
                    double* dkl_dev_out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || !p_dev || !dkl_dev_out) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_csr_dev: bad arguments");
@@ -778,10 +821,12 @@ int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, cons
   HS_TRY(hs_run_csr(ctx, p_dev, j_dev, x_dev, n_genes, dkl_dev_out));
   tm.stop();
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
                                int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_sel < 0 || n_perm <= 0 || !gene_ptr_dev || !out_dev)
@@ -796,10 +841,12 @@ int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t
   HS_TRY(hs_run_perm_seeded(ctx, gene_ptr_dev, n_sel, n_vals, val_dev, n_perm, seed, stream_base, out_dev));
   tm.stop();
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, int n_perm,
                            uint64_t seed, uint64_t stream_base, double* out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_sel < 0 || n_perm <= 0 || !gene_ptr || !out)
@@ -855,18 +902,22 @@ int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, 
     ub = ue;
   }
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_perm_sample(uint64_t seed, uint64_t stream, int64_t n, int64_t size, int index_base, int32_t* ids_out) {
+  try {
   if (n < 1 || n >= ((int64_t)1 << 31) || size < 0 || size > n || (size > 0 && !ids_out))
     return hs_fail(nullptr, HS_ERR_INVALID, "hs_perm_sample: need 1 <= n < 2^31 and 0 <= size <= n");
   const HsPrp prp = hs_prp_make(seed, stream, (uint32_t)n);
   for (int64_t i = 0; i < size; ++i) ids_out[i] = (int32_t)((int64_t)hs_prp_forward(prp, (uint32_t)i) + index_base);
   return HS_OK;
+  } HS_ABI_CATCH(nullptr)
 }
 
 int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, const float* val_dev,
                         const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_sel < 0 || n_perm <= 0 || !gene_ptr_dev || !out_dev)
@@ -880,9 +931,11 @@ int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
   HS_TRY(hs_run_perm_csr(ctx, gene_ptr_dev, n_sel, n_vals, val_dev, ind_dev, n_perm, index_base, out_dev));
   tm.stop();
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_dense_dev(hs_ctx* ctx, const float* expr_dev, int64_t n_genes, int64_t ld, double* dkl_dev_out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || ld < n_genes || !expr_dev || !dkl_dev_out)
@@ -891,10 +944,12 @@ int hs_dkl_dense_dev(hs_ctx* ctx, const float* expr_dev, int64_t n_genes, int64_
   HS_TRY(hs_run_dense_f32(ctx, expr_dev, n_genes, ld, dkl_dev_out));
   tm.stop();
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_dense_dev(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm, int index_base,
                           double* out_dev) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (!v_dev || !perm_dev || !out_dev || n_perm <= 0)
@@ -903,10 +958,12 @@ int hs_dkl_perm_dense_dev(hs_ctx* ctx, const float* v_dev, const int32_t* perm_d
   HS_TRY(hs_run_perm_dense(ctx, v_dev, perm_dev, n_perm, index_base, out_dev));
   tm.stop();
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_dense_seeded_dev(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed, uint64_t stream_base,
                                  double* out_dev) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (!v_dev || !out_dev || n_perm <= 0)
@@ -915,10 +972,12 @@ int hs_dkl_perm_dense_seeded_dev(hs_ctx* ctx, const float* v_dev, int n_perm, ui
   HS_TRY(hs_run_perm_dense_seeded(ctx, v_dev, n_perm, seed, stream_base, out_dev));
   tm.stop();
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t seed, uint64_t stream_base,
                              double* out) {
+  try {
   HS_TRY(need_density(ctx));
   HS_TRY(set_device(ctx));
   if (!v || !out || n_perm <= 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense_seeded: bad arguments");
@@ -935,19 +994,23 @@ int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t 
   HS_CUDA(ctx, cudaMemcpyAsync(out, ctx->out.p, sizeof(double) * (size_t)n_perm, cudaMemcpyDeviceToHost, st));
   HS_CUDA(ctx, cudaStreamSynchronize(st));
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_genes, int64_t n_cells,
                          double* mean_dev, double* sd_dev) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || n_cells < 1 || !p_dev || !mean_dev || !sd_dev)
     return hs_fail(ctx, HS_ERR_INVALID, "hs_row_stats_csr_dev: bad arguments");
   return hs_run_row_stats_f32(ctx, p_dev, x_dev, n_genes, n_cells, mean_dev, sd_dev);
+  } HS_ABI_CATCH(ctx)
 }
 
 int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, int64_t n_genes, int64_t n_cells,
                      double* mean_out, double* sd_out) {
+  try {
   if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
   HS_TRY(set_device(ctx));
   if (n_genes < 0 || n_cells < 1 || !p || !mean_out || !sd_out)
@@ -1003,6 +1066,7 @@ int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, i
   HS_CUDA(ctx, cudaMemcpyAsync(sd_out, sd_dev, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
   HS_CUDA(ctx, cudaStreamSynchronize(st));
   return HS_OK;
+  } HS_ABI_CATCH(ctx)
 }
 
 }  // extern "C"
