@@ -192,6 +192,18 @@ int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, i
 int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_genes,
                          int64_t n_cells, double* mean_dev, double* sd_dev);
 
+/* ---- CSC -> CSR (the step before the sparse path; optional) -------------------------------- */
+/* as(expression, "RsparseMatrix") (R/haystack_continuous.R:113-116) on the device: a stable counting sort by
+ * row id, column ids ascending inside every row, bit-reproducible.  cp: column pointers of the dgCMatrix
+ * (@p, int32 or int64, n_cols + 1 entries), ri: @i (0-based row ids), x: @x.  Outputs: the dgRMatrix slots
+ * p_out int64[n_rows + 1], j_out int32[nnz], x_out double[nnz].  At most 57344 rows per call. */
+int hs_csc_to_csr(hs_ctx* ctx, const void* cp, int cp_is_64, const int32_t* ri, const double* x,
+                  int64_t n_rows, int64_t n_cols, int64_t* p_out, int32_t* j_out, double* x_out);
+/* Device-resident form (int64 column pointers, fp32 values), producing what hs_dkl_csr_dev consumes. */
+int hs_csc_to_csr_dev(hs_ctx* ctx, const int64_t* cp_dev, const int32_t* ri_dev, const float* x_dev,
+                      int64_t n_rows, int64_t n_cols, int64_t* p_out_dev, int32_t* j_out_dev,
+                      float* x_out_dev);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Number of kernels of this library launched on this context since creation. */
 int64_t hs_launch_count(const hs_ctx* ctx);

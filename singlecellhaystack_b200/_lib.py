@@ -50,6 +50,8 @@ SIGNATURES = {
     "hs_density_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
     "hs_row_stats_csr": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _vp, _vp]),
     "hs_row_stats_csr_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "hs_csc_to_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "hs_csc_to_csr_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hs_launch_count": (_i64, [_vp]),
     "hs_last_timers": (_int, [_vp, C.POINTER(C.c_float), _int]),
     "hs_enable_timers": (_int, [_vp, _int]),

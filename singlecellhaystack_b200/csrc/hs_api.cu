@@ -273,7 +273,8 @@ void hs_destroy(hs_ctx* ctx) {
   DevBuf* bufs[] = {&ctx->D32, &ctx->Q, &ctx->sq, &ctx->rowmin, &ctx->nearest, &ctx->sel, &ctx->qpart,
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
-                    &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals, &ctx->perm_gp, &ctx->out_rand};
+                    &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals, &ctx->perm_gp, &ctx->out_rand,
+                    &ctx->conv_cp, &ctx->conv_ri, &ctx->conv_x, &ctx->conv_p, &ctx->conv_j, &ctx->conv_xo};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int k = 0; k < hs_ctx::kRing; ++k) {
@@ -1064,6 +1065,60 @@ int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, i
   }
   HS_CUDA(ctx, cudaMemcpyAsync(mean_out, mean_dev, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
   HS_CUDA(ctx, cudaMemcpyAsync(sd_out, sd_dev, sizeof(double) * (size_t)n_genes, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_csc_to_csr_dev(hs_ctx* ctx, const int64_t* cp_dev, const int32_t* ri_dev, const float* x_dev, int64_t n_rows,
+                      int64_t n_cols, int64_t* p_out_dev, int32_t* j_out_dev, float* x_out_dev) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (n_rows < 0 || n_cols < 0 || !cp_dev || !p_out_dev)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr_dev: bad arguments");
+  int64_t nnz = 0;
+  HS_CUDA(ctx, cudaMemcpyAsync(&nnz, cp_dev + n_cols, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (nnz < 0 || (nnz > 0 && (!ri_dev || !x_dev || !j_out_dev || !x_out_dev)))
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr_dev: bad arguments");
+  return hs_run_csc_to_csr_f32(ctx, cp_dev, ri_dev, x_dev, n_rows, n_cols, nnz, p_out_dev, j_out_dev, x_out_dev);
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_csc_to_csr(hs_ctx* ctx, const void* cp, int cp_is_64, const int32_t* ri, const double* x, int64_t n_rows,
+                  int64_t n_cols, int64_t* p_out, int32_t* j_out, double* x_out) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (n_rows < 0 || n_cols < 0 || !cp || !p_out) return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: bad arguments");
+  std::vector<int64_t> hp((size_t)n_cols + 1);
+  for (int64_t c = 0; c <= n_cols; ++c) hp[c] = cp_is_64 ? ((const int64_t*)cp)[c] : (int64_t)((const int32_t*)cp)[c];
+  if (hp[0] != 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: column pointers must start at 0");
+  for (int64_t c = 0; c < n_cols; ++c)
+    if (hp[c + 1] < hp[c]) return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: column pointers must be non-decreasing");
+  const int64_t nnz = hp[n_cols];
+  if (nnz > 0 && (!ri || !x || !j_out || !x_out)) return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: NULL array");
+  const size_t nz = (size_t)hs_max<int64_t>(nnz, 1);
+  HS_TRY(hs_ensure(ctx, ctx->conv_cp, sizeof(int64_t) * (size_t)(n_cols + 1)));
+  HS_TRY(hs_ensure(ctx, ctx->conv_ri, sizeof(int32_t) * nz));
+  HS_TRY(hs_ensure(ctx, ctx->conv_x, sizeof(double) * nz));
+  HS_TRY(hs_ensure(ctx, ctx->conv_p, sizeof(int64_t) * (size_t)(n_rows + 1)));
+  HS_TRY(hs_ensure(ctx, ctx->conv_j, sizeof(int32_t) * nz));
+  HS_TRY(hs_ensure(ctx, ctx->conv_xo, sizeof(double) * nz));
+  cudaStream_t st = ctx->stream;
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->conv_cp.p, hp.data(), sizeof(int64_t) * (size_t)(n_cols + 1), cudaMemcpyHostToDevice, st));
+  if (nnz > 0) {
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->conv_ri.p, ri, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->conv_x.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+  }
+  HS_TRY(hs_run_csc_to_csr_f64(ctx, (const int64_t*)ctx->conv_cp.p, (const int32_t*)ctx->conv_ri.p, (const double*)ctx->conv_x.p,
+                               n_rows, n_cols, nnz, (int64_t*)ctx->conv_p.p, (int32_t*)ctx->conv_j.p, (double*)ctx->conv_xo.p));
+  HS_CUDA(ctx, cudaMemcpyAsync(p_out, ctx->conv_p.p, sizeof(int64_t) * (size_t)(n_rows + 1), cudaMemcpyDeviceToHost, st));
+  if (nnz > 0) {
+    HS_CUDA(ctx, cudaMemcpyAsync(j_out, ctx->conv_j.p, sizeof(int32_t) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+    HS_CUDA(ctx, cudaMemcpyAsync(x_out, ctx->conv_xo.p, sizeof(double) * (size_t)nnz, cudaMemcpyDeviceToHost, st));
+  }
   HS_CUDA(ctx, cudaStreamSynchronize(st));
   return HS_OK;
   } HS_ABI_CATCH(ctx)

@@ -72,6 +72,7 @@ struct hs_ctx {
   DevBuf umma_flags;
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, (id, value) pairs, values of the selected rows
+  DevBuf conv_cp, conv_ri, conv_x, conv_p, conv_j, conv_xo;   // hs_csc_to_csr (host form): inputs and outputs
   DevBuf perm_gp, out_rand;               // hs_dkl_csr_randomized: gene pointers and results of the randomization batch
   bool skip_copy_fence = false;           // the caller guarantees that nothing in flight reads the upload buffers
   void* pinned = nullptr;      // small pinned host bounce buffer
@@ -124,6 +125,10 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
                      const void* pairs_dev = nullptr);
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
+int hs_run_csc_to_csr_f32(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const float* x, int64_t n_rows, int64_t n_cols,
+                          int64_t nnz, int64_t* p_out, int32_t* j_out, float* x_out);
+int hs_run_csc_to_csr_f64(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const double* x, int64_t n_rows, int64_t n_cols,
+                          int64_t nnz, int64_t* p_out, int32_t* j_out, double* x_out);
 int hs_run_row_stats_f64(hs_ctx* ctx, const int64_t* p_dev, const double* x_dev, int64_t n_rows, int64_t n_cells,
                          double* mean_dev, double* sd_dev);
 int hs_run_row_stats_f32(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_rows, int64_t n_cells,

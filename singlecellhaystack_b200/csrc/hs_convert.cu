@@ -1,0 +1,143 @@
+// CSC -> CSR on the device: as(expression, "RsparseMatrix") (R/haystack_continuous.R:113-116), the step
+// before the sparse scoring path (users hold a dgCMatrix; the path wants rows).
+//
+// A stable counting sort by row id that needs no atomics for the order: the columns are cut into blocks,
+// one CTA per block.
+//   1. k_csc_count     per block, how many entries every row has (shared-memory counters);
+//   2. k_csc_offsets   per row, exclusive prefix over the blocks -> where each block's entries of that row
+//                      start inside the row; the row totals give the CSR row pointers (cub exclusive sum);
+//   3. k_csc_scatter   per block, the columns are walked IN ORDER; the entries of one column belong to
+//                      distinct rows, so the threads of the CTA take them in parallel and bump the row's
+//                      cursor with a plain read-modify-write.  Column ids therefore come out ascending in
+//                      every row (what the slab kernel and R's dgRMatrix both want), bit-reproducibly.
+// Row counters live in shared memory (4 bytes per row: up to 56 000 rows per call).
+#include <cub/device/device_scan.cuh>
+#include <stdint.h>
+
+#include "hs_common.cuh"
+
+namespace {
+
+constexpr int kConvThreads = 512;
+
+template <typename P>
+__global__ void __launch_bounds__(kConvThreads)
+k_csc_count(const P* __restrict__ cp, const int32_t* __restrict__ ri, int64_t n_rows, int64_t n_cols, int cols_per_block,
+            uint32_t* __restrict__ hist /* [blocks][n_rows] */, int* __restrict__ flags) {
+  extern __shared__ uint32_t cnt[];
+  for (int64_t r = threadIdx.x; r < n_rows; r += kConvThreads) cnt[r] = 0;
+  __syncthreads();
+  const int64_t c0 = (int64_t)blockIdx.x * cols_per_block, c1 = hs_min<int64_t>(n_cols, c0 + cols_per_block);
+  const int64_t e0 = (int64_t)cp[c0], e1 = (int64_t)cp[c1];
+  bool bad = false;
+  for (int64_t e = e0 + threadIdx.x; e < e1; e += kConvThreads) {
+    const int32_t r = ri[e];
+    if (r < 0 || r >= n_rows) bad = true; else atomicAdd(&cnt[r], 1u);
+  }
+  if (bad) atomicOr(flags, 1);
+  __syncthreads();
+  uint32_t* out = hist + (int64_t)blockIdx.x * n_rows;
+  for (int64_t r = threadIdx.x; r < n_rows; r += kConvThreads) out[r] = cnt[r];
+  // (a block past the last column cannot exist: n_blocks is derived from cols_per_block)
+}
+
+// hist[b][r] := number of entries of row r in blocks < b; total[r] := row length
+__global__ void __launch_bounds__(256)
+k_csc_offsets(uint32_t* __restrict__ hist, int n_blocks, int64_t n_rows, int64_t* __restrict__ total) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_rows) return;
+  if (r == n_rows) {
+    total[r] = 0;   // slot of the exclusive sum's last element
+    return;
+  }
+  uint32_t run = 0;
+  for (int b = 0; b < n_blocks; ++b) {
+    const uint32_t c = hist[(int64_t)b * n_rows + r];
+    hist[(int64_t)b * n_rows + r] = run;
+    run += c;
+  }
+  total[r] = (int64_t)run;
+}
+
+template <typename P, typename TI, typename TO>
+__global__ void __launch_bounds__(kConvThreads)
+k_csc_scatter(const P* __restrict__ cp, const int32_t* __restrict__ ri, const TI* __restrict__ x, int64_t n_rows,
+              int64_t n_cols, int cols_per_block, const uint32_t* __restrict__ hist, const int64_t* __restrict__ p_out,
+              int32_t* __restrict__ j_out, TO* __restrict__ x_out) {
+  extern __shared__ uint32_t pos[];   // cursor of every row inside the row, for this block
+  const uint32_t* mine = hist + (int64_t)blockIdx.x * n_rows;
+  for (int64_t r = threadIdx.x; r < n_rows; r += kConvThreads) pos[r] = mine[r];
+  __syncthreads();
+  const int64_t c0 = (int64_t)blockIdx.x * cols_per_block, c1 = hs_min<int64_t>(n_cols, c0 + cols_per_block);
+  for (int64_t c = c0; c < c1; ++c) {
+    const int64_t e0 = (int64_t)cp[c], e1 = (int64_t)cp[c + 1];
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += kConvThreads) {
+      const int32_t r = ri[e];
+      if (r < 0 || r >= n_rows) continue;            // flagged by the counting pass
+      const uint32_t k = pos[r];                     // rows are distinct inside a column: no race
+      pos[r] = k + 1;
+      const int64_t o = p_out[r] + k;
+      j_out[o] = (int32_t)c;
+      x_out[o] = (TO)x[e];
+    }
+    __syncthreads();                                 // the next column may revisit the same rows
+  }
+}
+
+}  // namespace
+
+// cp: column pointers (int32 or int64, n_cols + 1), ri: 0-based row ids (ascending inside a column, distinct),
+// x: values.  p_out int64[n_rows + 1], j_out int32[nnz], x_out[nnz].  All device pointers.
+template <typename P, typename TI, typename TO>
+static int convert_impl(hs_ctx* ctx, const P* cp, const int32_t* ri, const TI* x, int64_t n_rows, int64_t n_cols,
+                        int64_t nnz, int64_t* p_out, int32_t* j_out, TO* x_out) {
+  cudaStream_t st = ctx->stream;
+  const size_t smem = sizeof(uint32_t) * (size_t)hs_max<int64_t>(n_rows, 1);
+  if (smem > 224 * 1024)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: %lld rows exceed the 57344 a call can take (convert row blocks "
+                   "separately or on the host)", (long long)n_rows);
+  // column blocks: enough CTAs to fill the machine several times over, at most 1024 histograms
+  int n_blocks = (int)hs_min<int64_t>(hs_max<int64_t>(n_cols, 1), hs_min<int64_t>(1024, (int64_t)ctx->sm_count * 8));
+  const int cols_per_block = (int)((hs_max<int64_t>(n_cols, 1) + n_blocks - 1) / n_blocks);
+  n_blocks = (int)((hs_max<int64_t>(n_cols, 1) + cols_per_block - 1) / cols_per_block);
+  size_t scan_ws = 0;
+  HS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, scan_ws, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(n_rows + 1), st));
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t hist_b = up256(sizeof(uint32_t) * (size_t)n_blocks * (size_t)hs_max<int64_t>(n_rows, 1));
+  const size_t total_b = up256(sizeof(int64_t) * (size_t)(n_rows + 1));
+  HS_TRY(hs_ensure(ctx, ctx->spmm_ws, 256 + hist_b + total_b + scan_ws + 256));
+  char* w = (char*)ctx->spmm_ws.p;
+  int* flags = (int*)w;                 w += 256;
+  uint32_t* hist = (uint32_t*)w;        w += hist_b;
+  int64_t* total = (int64_t*)w;         w += total_b;
+  void* cub_ws = w;
+  HS_CUDA(ctx, cudaMemsetAsync(flags, 0, 256, st));
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_csc_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  HS_CUDA(ctx, cudaFuncSetAttribute(k_csc_scatter<P, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_csc_count<P><<<n_blocks, kConvThreads, smem, st>>>(cp, ri, n_rows, n_cols, cols_per_block, hist, flags);
+  HS_LAUNCH_CHECK(ctx);
+  k_csc_offsets<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(hist, n_blocks, n_rows, total);
+  HS_LAUNCH_CHECK(ctx);
+  HS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_ws, scan_ws, total, p_out, (int)(n_rows + 1), st));
+  ctx->launches++;
+  if (nnz > 0) {
+    k_csc_scatter<P, TI, TO><<<n_blocks, kConvThreads, smem, st>>>(cp, ri, x, n_rows, n_cols, cols_per_block, hist, p_out,
+                                                                  j_out, x_out);
+    HS_LAUNCH_CHECK(ctx);
+  }
+  int bad = 0;
+  HS_CUDA(ctx, cudaMemcpyAsync(&bad, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (bad) return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: row ids outside [0, n_rows)");
+  return HS_OK;
+}
+
+int hs_run_csc_to_csr_f32(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const float* x, int64_t n_rows, int64_t n_cols,
+                          int64_t nnz, int64_t* p_out, int32_t* j_out, float* x_out) {
+  return convert_impl<int64_t, float, float>(ctx, cp, ri, x, n_rows, n_cols, nnz, p_out, j_out, x_out);
+}
+
+int hs_run_csc_to_csr_f64(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const double* x, int64_t n_rows, int64_t n_cols,
+                          int64_t nnz, int64_t* p_out, int32_t* j_out, double* x_out) {
+  return convert_impl<int64_t, double, double>(ctx, cp, ri, x, n_rows, n_cols, nnz, p_out, j_out, x_out);
+}

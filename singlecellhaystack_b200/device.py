@@ -127,6 +127,27 @@ class DeviceContext:
         self._check(self._lib.hs_density_shape(self._h, C.byref(n), C.byref(g)), "hs_density_shape")
         return int(n.value), int(g.value)
 
+    # -- CSC -> CSR (R/haystack_continuous.R:113-116) -------------------------------------------
+    def csc_to_csr(self, cp, ri, x, n_rows: int, n_cols: int):
+        """hs_csc_to_csr: dgCMatrix slots (p, i, x) -> dgRMatrix slots (p int64, j int32, x fp64), column ids
+        ascending inside every row."""
+        cp = np.ascontiguousarray(cp)
+        if cp.dtype not in (np.int32, np.int64):
+            cp = cp.astype(np.int64)
+        ri = np.ascontiguousarray(ri, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        nnz = int(cp[-1]) if cp.size else 0
+        p_out = np.empty(int(n_rows) + 1, dtype=np.int64)
+        j_out = np.empty(nnz, dtype=np.int32)
+        x_out = np.empty(nnz, dtype=np.float64)
+        self._check(self._lib.hs_csc_to_csr(self._h, _ptr(cp), int(cp.dtype == np.int64), _ptr(ri), _ptr(x), int(n_rows),
+                                            int(n_cols), _ptr(p_out), _ptr(j_out), _ptr(x_out)), "hs_csc_to_csr")
+        return p_out, j_out, x_out
+
+    def csc_to_csr_dev(self, cp_dev, ri_dev, x_dev, n_rows: int, n_cols: int, p_out_dev, j_out_dev, x_out_dev):
+        self._check(self._lib.hs_csc_to_csr_dev(self._h, _dptr(cp_dev), _dptr(ri_dev), _dptr(x_dev), int(n_rows), int(n_cols),
+                                                _dptr(p_out_dev), _dptr(j_out_dev), _dptr(x_out_dev)), "hs_csc_to_csr_dev")
+
     # -- row statistics (R/haystack_continuous.R:57-74) ---------------------------------------
     def row_stats_csr(self, p, x, n_cells: int):
         """hs_row_stats_csr: (mean, sd) per CSR row, sd with the n-1 denominator and the implicit zeros

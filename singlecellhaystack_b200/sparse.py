@@ -102,11 +102,15 @@ def as_CsparseMatrix(m, rownames=None, colnames=None) -> dgCMatrix:
     return dgCMatrix(p=c.indptr, i=c.indices, x=c.data, Dim=c.shape, rownames=rownames, colnames=colnames)
 
 
-def as_RsparseMatrix(m, rownames=None, colnames=None) -> dgRMatrix:
+def as_RsparseMatrix(m, rownames=None, colnames=None, ctx=None) -> dgRMatrix:
     """as(m, "RsparseMatrix"): dgCMatrix / scipy sparse / dense -> dgRMatrix with ascending j per row
-    (counting sort over the stored entries; stored zeros of a sparse input are kept, as Matrix does)."""
+    (counting sort over the stored entries; stored zeros of a sparse input are kept, as Matrix does).
+    With a DeviceContext `ctx`, a dgCMatrix is converted on the GPU (hs_csc_to_csr): same slots, bit for bit."""
     if isinstance(m, dgRMatrix):
         return m
+    if isinstance(m, dgCMatrix) and ctx is not None and m.Dim[0] <= 57344:
+        p, j, x = ctx.csc_to_csr(m.p, m.i, m.x, m.Dim[0], m.Dim[1])
+        return dgRMatrix(p=p, j=j, x=x, Dim=m.Dim, rownames=rownames or m.rownames, colnames=colnames or m.colnames)
     if isinstance(m, dgCMatrix):
         nrow, ncol = m.Dim
         counts = np.bincount(m.i, minlength=nrow)

@@ -115,3 +115,56 @@ def test_front_door_with_device_row_stats(ctx, toy):
     same = np.array_equal(res["info"]["randomization"]["genes_to_randomize"], toy["full_genes_to_randomize"] + 1)
     # identical selection -> identical null sample -> identical p-values; tied genes swapped -> another null sample
     assert np.max(np.abs(res["results"]["log.p.vals"].values - toy["full_log_p"])) < (1e-3 if same else 1.5)
+
+
+def test_csc_to_csr_matches_host_conversion(ctx, toy):
+    """hs_csc_to_csr (as(expression, "RsparseMatrix"), R/haystack_continuous.R:113-116): the dgRMatrix slots
+    must equal the host conversion bit for bit -- row pointers, ascending column ids, values."""
+    from singlecellhaystack_b200 import sparse as sp_
+    cases = [sp_.as_CsparseMatrix(toy["expression"].astype(np.float64))]
+    rng = np.random.default_rng(12)
+    a = rng.random((300, 1500)) * (rng.random((300, 1500)) < 0.07)
+    a[17] = 0.0                      # empty row
+    a[:, 40:90] = 0.0                # a run of empty columns
+    a[250] = 1.5                     # a full row
+    cases.append(sp_.as_CsparseMatrix(a))
+    cases.append(sp_.as_CsparseMatrix(np.zeros((5, 7))))          # nothing stored
+    for m in cases:
+        want = sp_.as_RsparseMatrix(m)
+        got = sp_.as_RsparseMatrix(m, ctx=ctx)
+        np.testing.assert_array_equal(got.p, want.p)
+        np.testing.assert_array_equal(got.j, want.j)
+        np.testing.assert_array_equal(got.x, want.x)
+        again = ctx.csc_to_csr(m.p.astype(np.int32), m.i, m.x, m.Dim[0], m.Dim[1])     # int32 pointers, repeat
+        np.testing.assert_array_equal(again[1], want.j)
+    from singlecellhaystack_b200.device import HaystackLibraryError
+    m = cases[1]
+    bad_i = m.i.copy()
+    bad_i[3] = 300
+    with pytest.raises(HaystackLibraryError, match="row ids outside"):
+        ctx.csc_to_csr(m.p, bad_i, m.x, 300, 1500)
+
+
+def test_csc_to_csr_device_form_feeds_the_scoring(ctx, toy):
+    import torch
+    from oracle import haystack_oracle as ho
+    from singlecellhaystack_b200 import sparse as sp_
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ctx.density(xs, toy["grid100"])
+    m = sp_.as_CsparseMatrix(toy["expression"].astype(np.float64))
+    dev = torch.device("cuda:0")
+    cp = torch.as_tensor(m.p.astype(np.int64), device=dev)
+    ri = torch.as_tensor(m.i, device=dev)
+    x = torch.as_tensor(m.x.astype(np.float32), device=dev)
+    p_out = torch.empty(501, dtype=torch.int64, device=dev)
+    j_out = torch.empty(ri.numel(), dtype=torch.int32, device=dev)
+    x_out = torch.empty(ri.numel(), dtype=torch.float32, device=dev)
+    ctx.use_torch_stream(torch.cuda.current_stream())
+    try:
+        ctx.csc_to_csr_dev(cp, ri, x, 500, 601, p_out, j_out, x_out)
+        dkl = torch.empty(500, dtype=torch.float64, device=dev)
+        ctx.dkl_csr_dev(p_out, j_out, x_out, dkl)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_stream(None)
+    assert _rel(dkl.cpu().numpy(), toy["dkl100"]) < RTOL
