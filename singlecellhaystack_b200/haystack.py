@@ -145,7 +145,7 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
                               n_genes_to_randomize=100, selection_method_genes_to_randomize="heavytails",
                               grid_coord=None, spline_method="ns", *, gene_names=None, rng=None,
                               perm_source=None, cv_folds=None, row_stats=None, ctx=None, device=0,
-                              verbose=True, return_densities=True):
+                              verbose=True, return_densities=True, convert_on_device=False):
     """The main Haystack function for continuous expression in a high-dimensional space
     (R/haystack_continuous.R:27-339).  Positional / keyword arguments up to `spline_method` are the
     reference's; the keyword-only ones are host plumbing:
@@ -161,6 +161,7 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
                    Matrix::rowMeans / rowSds, so the integer gene selection is R's even for tied genes);
                    or "device": sparse input is reduced by hs_row_stats_csr (fp64, two-pass) on the GPU
       ctx/device   an existing DeviceContext, or the CUDA device ordinal to create one on
+      convert_on_device  dgCMatrix -> dgRMatrix (:113-116) with hs_csc_to_csr on the GPU instead of on the host
       return_densities  fill info["densities"] (N x G fp64, 800 MB at 1M cells) as the reference does
     """
     from .device import DeviceContext
@@ -196,10 +197,16 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
     if sparse_in:
         # the reference computes the statistics first and converts afterwards (:113-116); the order is
         # immaterial for the numbers, and one CSR pass serves both
+        own_ctx = False
         if isinstance(expression, _sparse.dgCMatrix) or not isinstance(expression, _sparse.dgRMatrix):
             _message(verbose, "### converting expression data from dgCMatrix to dgRMatrix")
-        expression = _sparse.as_RsparseMatrix(expression)
-    own_ctx = False
+            if convert_on_device:             # hs_csc_to_csr instead of the host counting sort
+                if ctx is None:
+                    ctx, own_ctx = DeviceContext(device), True
+                expression = _sparse.as_CsparseMatrix(expression)
+        expression = _sparse.as_RsparseMatrix(expression, ctx=ctx if convert_on_device else None)
+    else:
+        own_ctx = False
     if isinstance(row_stats, str):
         if row_stats != "device":
             raise ValueError("row_stats must be a (mean, sd) pair, None or 'device'")

@@ -263,3 +263,20 @@ def test_toy_full_path_with_device_draws(ctx, toy):
     gold = toy["full_KLD_rand"]
     z = (rnd["KLD_rand"].mean(axis=1) - gold.mean(axis=1)) / (gold.std(axis=1, ddof=1) * np.sqrt(2 / 100))
     assert np.abs(z).max() < 5 and abs(z.mean()) < 0.5
+
+
+def test_convert_on_device_gives_identical_results(ctx, toy):
+    """haystack(convert_on_device=True): the dgCMatrix -> dgRMatrix step on the GPU (hs_csc_to_csr) yields the
+    same slots as the host conversion, hence identical results."""
+    seed = int(toy["seed"])
+    expr = toy["expression"]
+    kw = dict(grid_coord=toy["grid100"], perm_source=synth.perm_source(seed),
+              row_stats=ho.row_mean_sd(ho.RowSparse.from_dense(expr)),
+              cv_folds=(synth.cv_folds(seed, 0, 100), synth.cv_folds(seed, 1, 100)), ctx=ctx, verbose=False)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = hh.haystack(toy["coord"], sp.as_CsparseMatrix(expr), **kw)
+        b = hh.haystack(toy["coord"], sp.as_CsparseMatrix(expr), convert_on_device=True, **kw)
+    np.testing.assert_array_equal(a["results"]["D_KL"].values, b["results"]["D_KL"].values)
+    # (the ids-given randomization sums in atomics order: its scores repeat to ~1e-8, not bit for bit)
+    np.testing.assert_allclose(a["results"]["log.p.vals"].values, b["results"]["log.p.vals"].values, rtol=0, atol=1e-6)
