@@ -24,9 +24,11 @@
  *     hs_last_error(ctx) (or hs_last_error(NULL) when no context exists).  Nothing throws or
  *     longjmps across this boundary.
  *   - The caller owns every host buffer for the duration of the call only.  The context owns
- *     all device memory and streams.  The library draws NO random numbers: permutation indices
- *     are inputs (the R shim produces them with sample()/sample.int(), so set.seed()
- *     reproducibility is the host's).
+ *     all device memory and streams.  The ids-given entry points (hs_dkl_perm_dense,
+ *     hs_dkl_perm_csr) draw NO random numbers: permutation indices are inputs (the R shim produces
+ *     them with sample()/sample.int(), so set.seed() reproducibility is the host's).  The *_seeded
+ *     entry points, hs_dkl_csr_randomized and hs_perm_sample draw from a keyed permutation that is
+ *     a function of (seed, stream) only -- reproducible, but not R's Mersenne-Twister stream.
  *   - One context per process and device (one process per GPU; multi-GPU gene sharding is done
  *     by the host layer with torch.distributed/NCCL).
  *   - There is no CPU fallback: every entry point fails with HS_ERR_CUDA when no sm_100 device

@@ -11,6 +11,7 @@ The GPU box has no /root/reference, so tests read only the committed .npz.  Cont
   and the oracle's outputs for those grids: bandwidth, Q, nearest, D_KL (dense and sparse rows
   agree), plus the sparse randomization matrix and log10 p-values for grid100 with the
   hash-generated permutations / folds of singlecellhaystack_b200.synth (seed below).
+Also writes tests/golden/toy_r1234.npz (see make_r_golden): the vignette call on R's own random stream.
 """
 from __future__ import annotations
 
@@ -65,11 +66,40 @@ def main():
     dst = ROOT / "tests" / "golden"
     dst.mkdir(parents=True, exist_ok=True)
     np.savez_compressed(dst / "toy.npz", **out)
+    make_r_golden(coord, expr, toy["gene_names"], dst)
     top = np.argsort(res["log_p_vals"])[:10]
     print("top genes (oracle, synth grid):")
     for i in top:
         print(f"  {toy['gene_names'][i]:>9s}  D_KL {res['D_KL'][i]:.6f}  log.p {res['log_p_vals'][i]:.4f}")
     print("wrote", dst / "toy.npz", (dst / "toy.npz").stat().st_size, "bytes")
+
+
+def make_r_golden(coord, expr, gene_names, dst):
+    """tests/golden/toy_r1234.npz: the reference's vignette call `set.seed(1234); haystack(dat.tsne, dat.expression)`
+    (docs/articles/a01_toy_example.html) replayed on the restated R generator / k-means (oracle/r_base): the grid R's
+    kmeans() picks, the selected genes, the CV folds, a checksum per gene of the 100 x 601 permutation ids (the ids
+    themselves are regenerated from the seed: 6 M integers are not a small fixture) and the oracle's results, which
+    tests/test_r_parity_cpu.py holds against the table the reference printed."""
+    from oracle import r_base as rb
+    rng = rb.RRng(1234)
+    xs, _, _ = ho.scale_coords(coord)
+    grid = rb.get_grid_points(xs, rng, "centroid", 100)
+    mean, sd = ho.row_mean_sd(expr)
+    cv = (sd + 1e-300) / (mean + 1e-300)
+    genes = ho.select_genes_to_randomize(cv, 100, "heavytails")
+    perms = {int(g): rng.sample_int(601, 601, count=100) for g in genes}
+    folds_mean = rng.sample(np.resize(np.arange(1, 11), 100))
+    folds_sd = rng.sample(np.resize(np.arange(1, 11), 100))
+    res = ho.haystack_continuous_highD(coord, expr, grid, lambda kind, gene, n, size, count: perms[gene],
+                                       folds_mean, folds_sd)
+    chk = np.array([int(perms[int(g)].astype(np.int64).dot(np.arange(1, 602)).sum() % (2 ** 31)) for g in genes])
+    np.savez_compressed(dst / "toy_r1234.npz", seed=np.int64(1234), grid_scaled=grid,
+                        grid_coordinates=res["grid_coordinates"], genes_to_randomize=genes.astype(np.int64),
+                        folds_mean=folds_mean.astype(np.int32), folds_sd=folds_sd.astype(np.int32),
+                        perm_checksums=chk, bandwidth=np.float64(res["bandwidth"]), Q=res["Q"], D_KL=res["D_KL"],
+                        KLD_rand=res["KLD_rand"], log_p_vals=res["log_p_vals"], log_p_adj=res["log_p_adj"],
+                        best_df=np.array([res["fit"]["mean_model"]["best_df"], res["fit"]["sd_model"]["best_df"]]))
+    print("wrote", dst / "toy_r1234.npz", (dst / "toy_r1234.npz").stat().st_size, "bytes")
 
 
 if __name__ == "__main__":

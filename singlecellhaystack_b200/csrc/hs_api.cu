@@ -274,7 +274,7 @@ void hs_destroy(hs_ctx* ctx) {
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
                     &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals, &ctx->perm_gp, &ctx->out_rand,
-                    &ctx->conv_cp, &ctx->conv_ri, &ctx->conv_x, &ctx->conv_p, &ctx->conv_j, &ctx->conv_xo};
+                    &ctx->tile_ent, &ctx->tile_ws, &ctx->conv_cp, &ctx->conv_ri, &ctx->conv_x, &ctx->conv_p, &ctx->conv_j, &ctx->conv_xo};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int k = 0; k < hs_ctx::kRing; ++k) {
@@ -692,10 +692,15 @@ int hs_dkl_csr_randomized(hs_ctx* ctx, const void* p, int p_is_64, const int32_t
     HS_TRY(hs_run_perm_seeded(ctx, (const int64_t*)ctx->perm_gp.p, n_sel, nv, (const float*)ctx->perm_vals.p, n_perm, seed,
                               stream_base, (double*)ctx->out_rand.p));
     // the batch reads none of the CSR upload buffers: the uploads need not wait for it
-    ctx->skip_copy_fence = true;
-    const int rc = dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out);
-    ctx->skip_copy_fence = false;
-    HS_TRY(rc);
+    struct FenceGuard {   // cleared on every exit path, exceptions included
+      hs_ctx* c;
+      explicit FenceGuard(hs_ctx* cc) : c(cc) { c->skip_copy_fence = true; }
+      ~FenceGuard() { c->skip_copy_fence = false; }
+    };
+    {
+      FenceGuard guard(ctx);
+      HS_TRY(dkl_csr_any(ctx, p, p_is_64, j, x, false, n_genes, dkl_out));
+    }
     HS_CUDA(ctx, cudaMemcpyAsync(rand_out, ctx->out_rand.p, sizeof(double) * (size_t)(n_sel * n_perm), cudaMemcpyDeviceToHost, st));
     HS_CUDA(ctx, cudaStreamSynchronize(st));
     return HS_OK;

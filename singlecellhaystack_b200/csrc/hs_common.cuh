@@ -70,6 +70,7 @@ struct hs_ctx {
   DevBuf dtile_hi, dtile_lo;   // fp16 hi / lo density operands pre-tiled for the tensor-core kernels
   bool tiles_valid = false;    // the tiles match the resident density matrix
   DevBuf umma_flags;
+  DevBuf tile_ent, tile_ws;    // tile path of the sparse contraction: tile-major entries, cuts / region / tile tables
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, (id, value) pairs, values of the selected rows
   DevBuf conv_cp, conv_ri, conv_x, conv_p, conv_j, conv_xo;   // hs_csc_to_csr (host form): inputs and outputs
@@ -121,10 +122,17 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
 // slab-staged sparse contraction (hs_spmm.cu); see there for the arguments
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out,
-                     const void* pairs_dev = nullptr);
+                     int out_n_perm, int64_t out_n_sel, bool allow_tiles, const int** flag_dev_out,
+                     const void* pairs_dev = nullptr, int64_t nnz_hint = -1, bool tile_only = false);
+// tensor-core tile path of the sparse contraction (hs_tiles.cu)
+bool hs_tile_path_enabled(const hs_ctx* ctx);
+int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_rows_dev, int64_t n_rows,
+                     int64_t nnz_total, const int32_t* cols_dev, const float* vals_dev, const void* pairs_dev,
+                     int col_base, double* out_dev, int out_n_perm, int64_t out_n_sel, int* flags);
+int hs_ensure_density_tiles(hs_ctx* ctx);   // hs_umma.cu: pre-tiled fp16 hi / lo density operands
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
-                       const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev);
+                       const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev,
+                       const int** fallback_flag_out);
 int hs_run_csc_to_csr_f32(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const float* x, int64_t n_rows, int64_t n_cols,
                           int64_t nnz, int64_t* p_out, int32_t* j_out, float* x_out);
 int hs_run_csc_to_csr_f64(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const double* x, int64_t n_rows, int64_t n_cols,
@@ -146,10 +154,6 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
                       const int32_t* perm_dev, int index_base, int64_t n_rows, double* out_dev,
                       const int** flag_dev_out);
 bool hs_umma_disabled();   // HS_DISABLE_UMMA=1 forces the SIMT kernels (A/B comparisons)
-int hs_csr_umma_segments(const hs_ctx* ctx, int64_t n_dense);   // cell segments hs_run_csr_umma will use
-int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
-                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP,
-                    int64_t seg_stride, int n_seg, int* flags);
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
                       int index_base, double* out_dev);

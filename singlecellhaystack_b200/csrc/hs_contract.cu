@@ -317,7 +317,7 @@ int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const fl
   // slab-staged kernel; rows it flags (ids not ascending / negative) are redone by the gather kernel,
   // chained on the device-side flag so no host round trip is needed
   const int* flag = nullptr;
-  HS_TRY(hs_run_slab_spmm(ctx, false, p_dev, n_rows, 1, j_dev, x_dev, 0, out_dev, 0, 0, /*allow_umma=*/true, &flag));
+  HS_TRY(hs_run_slab_spmm(ctx, false, p_dev, n_rows, 1, j_dev, x_dev, 0, out_dev, 0, 0, /*allow_tiles=*/true, &flag));
   return launch_rows_gather<false>(ctx, p_dev, j_dev, x_dev, n_rows, 1, n_rows, 0, flag, out_dev);
 }
 
@@ -325,8 +325,15 @@ int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int
                     const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
   // bucket the ids by slab and use the slab kernel; gather straight from L2/HBM only when the cell
   // axis is too long for the bucketing histogram
-  const int rc = hs_run_perm_sorted(ctx, gene_ptr_dev, n_sel, n_vals_total, val_dev, ind_dev, n_perm, index_base, out_dev);
-  if (rc != -1) return rc;
+  const int* flag = nullptr;
+  const int rc = hs_run_perm_sorted(ctx, gene_ptr_dev, n_sel, n_vals_total, val_dev, ind_dev, n_perm, index_base, out_dev,
+                                    &flag);
+  if (rc != -1) {
+    if (rc != HS_OK || !flag) return rc;
+    // tensor-core tile path: rows it could not take (ids outside [0, N), values beyond fp16) are gathered instead
+    return launch_rows_gather<true>(ctx, gene_ptr_dev, ind_dev, val_dev, n_sel * (int64_t)n_perm, n_perm, n_sel,
+                                    index_base, flag, out_dev);
+  }
   return launch_rows_gather<true>(ctx, gene_ptr_dev, ind_dev, val_dev, n_sel * (int64_t)n_perm, n_perm, n_sel,
                                   index_base, nullptr, out_dev);
 }

@@ -209,6 +209,7 @@ struct SpmmParams {
   int64_t seg_stride;      // doubles between the segments of P64
   int ldP;
   int* flags;              // bit 0: order violation / negative id -> caller falls back
+  const int* run_if_flag;  // when set: the kernel only runs if bit 0 of this word is set (fallback of the tile path)
 };
 
 template <int NV, int K>
@@ -234,6 +235,7 @@ __device__ __forceinline__ void flush_row(float (&acc)[4 * NV], double* __restri
 template <int NV, int K, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
+  if (p.run_if_flag && !(*p.run_if_flag & 1)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = p.slab_cells, ldD = p.ldD;
   const size_t slab_bytes = (size_t)S * ldD * sizeof(float);
@@ -507,6 +509,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_slab_spmm(const SpmmParams p
 
   // ---------------- final flush, left-over (out of range) ids ----------------
   flush_rows(__ballot_sync(0xffffffffu, lane < K && row >= 0 && cnt > 0));
+  // Cell segments (n_seg > 1) start at a binary search, which presumes ascending ids.  Every consumed entry was
+  // checked against its slab, so the row is scored correctly iff the segments' runs tile it: this segment must
+  // have stopped exactly where the next one's search starts.  Anything else (ids out of order) -> fallback.
+  if (p.n_seg > 1 && blockIdx.y + 1 < gridDim.y && lane < K && row >= 0) {
+    int lo = 0, hi = len;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const int cm = p.pairs ? (int)p.pairs[coff + mid].x : p.cols[coff + mid];
+      if ((int64_t)cm - p.col_base < c_end) lo = mid + 1; else hi = mid;
+    }
+    if (lo != pos) violation = true;
+  }
   // ids >= N are never consumed: poison the row like the gather kernel does (last segment only)
   if (lane < K && row >= 0 && blockIdx.y == gridDim.y - 1 && pos < len) P64[(int64_t)row * p.ldP] = NAN;
   if (__any_sync(0xffffffffu, violation) && lane == 0) atomicOr(p.flags, 1);
@@ -517,8 +531,9 @@ template <int NACC>
 __global__ void __launch_bounds__(256)
 k_p64_epilogue(const double* __restrict__ P64, int n_seg, int64_t seg_stride, int64_t n_rows, int ldP, int G,
                const double* __restrict__ Q, int n_perm, int64_t n_sel, const int* __restrict__ flags,
-               double* __restrict__ out) {
+               const int* __restrict__ run_if_flag, double* __restrict__ out) {
   if (*flags & 1) return;   // the fallback kernel produces the output
+  if (run_if_flag && !(*run_if_flag & 1)) return;   // the tile path produced it
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_rows) return;
@@ -723,8 +738,8 @@ int hs_slab_cells(const hs_ctx* ctx) {
 // chain the order-independent fallback without a host round trip.
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,
                      const int32_t* cols_dev, const float* vals_dev, int col_base, double* out_dev,
-                     int out_n_perm, int64_t out_n_sel, bool allow_umma, const int** flag_dev_out,
-                     const void* pairs_dev) {
+                     int out_n_perm, int64_t out_n_sel, bool allow_tiles, const int** flag_dev_out,
+                     const void* pairs_dev, int64_t nnz_hint, bool tile_only) {
   const int64_t n_rows = perm ? n_units * (int64_t)n_perm : n_units;
   if (n_rows <= 0) return HS_OK;
   if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many rows (%lld) for one call", (long long)n_rows);
@@ -764,24 +779,29 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
                                                          (int)n_rows, 0, 32, st));
   ctx->launches += 3;   // cub: histogram + onesweep passes (counted once as a family)
 
-  // ---- the densest rows go to the tensor cores (hs_umma.cu): above a few % non-zeros the dense-equivalent
-  //      MMA work is cheaper than gathering a density row per non-zero.  Whole 128-row tiles only. ----
-  int64_t n_dense = 0;
-  if (allow_umma && !perm && G <= 128 && !hs_umma_disabled()) {
-    // Off unless asked for: with the scalar scatter producer the tensor path does not beat the slab kernel
-    // yet (profiles/README.md); HS_UMMA_MIN_DENSITY=<fraction> enables it.
-    const char* e = getenv("HS_UMMA_MIN_DENSITY");
-    const double min_density = (e && *e) ? atof(e) : 2.0;
-    const uint32_t thr = (uint32_t)hs_max<int64_t>(32, (int64_t)ceil(min_density * (double)ctx->N));
-    int n_ge = 0;
-    if (min_density <= 1.0) {
-      k_count_ge<<<1, 1, 0, st>>>(keys_out, n_rows, thr, flags + 1);
-      HS_LAUNCH_CHECK(ctx);
-      HS_CUDA(ctx, cudaMemcpyAsync(&n_ge, flags + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+  // ---- rows with ascending ids and G <= 128: the tensor-core tile path (hs_tiles.cu) scores the call; the slab
+  //      kernel below is then only its fallback (fp16 overflow of a value, ids not ascending), chained on a flag ----
+  const int* run_if = nullptr;
+  if (allow_tiles && !perm && hs_tile_path_enabled(ctx) && (n_rows + 127) / 128 <= 65535) {
+    int64_t nnz_total = nnz_hint;
+    if (nnz_total < 0) {
+      int64_t ends[2] = {0, 0};
+      HS_CUDA(ctx, cudaMemcpyAsync(&ends[0], ptr_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+      HS_CUDA(ctx, cudaMemcpyAsync(&ends[1], ptr_dev + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
       HS_CUDA(ctx, cudaStreamSynchronize(st));
+      nnz_total = ends[1] - ends[0];
+      if (nnz_total < 0) return hs_fail(ctx, HS_ERR_INVALID, "row pointers must be non-decreasing");
     }
-    n_dense = ((int64_t)n_ge / 128) * 128;
+    int* tile_flag = flags + 2;
+    HS_TRY(hs_run_tile_spmm(ctx, ptr_dev, rows_out, n_rows, nnz_total, cols_dev, vals_dev, pairs_dev, col_base, out_dev,
+                            out_n_perm, out_n_sel, tile_flag));
+    run_if = tile_flag;
+    if (tile_only) {          // the caller chains its own fallback on the tile flag
+      if (flag_dev_out) *flag_dev_out = tile_flag;
+      return HS_OK;
+    }
   }
+  const int64_t n_dense = 0;
 
   // ---- the remaining rows: slab kernel ----
   const int64_t n_sub = n_rows - n_dense;
@@ -824,14 +844,10 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   n_seg = (int)((ctx->N + seg_cells - 1) / seg_cells);
   // fp64 column sums: one [n_rows][ldP] block per cell segment of either kernel (single writer per block
   // and row; the epilogue adds the blocks in order, so repeated calls are bit-identical)
-  const int n_seg_umma = n_dense > 0 ? hs_csr_umma_segments(ctx, n_dense) : 0;
-  const int n_seg_all = hs_max(n_seg, hs_max(n_seg_umma, 1));
+  const int n_seg_all = hs_max(n_seg, 1);
   const int64_t seg_stride = n_rows * (int64_t)ldP;
   HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_seg_all * (size_t)seg_stride));
   HS_CUDA(ctx, cudaMemsetAsync(ctx->part.p, 0, sizeof(double) * (size_t)n_seg_all * (size_t)seg_stride, st));
-  if (n_dense > 0)
-    HS_TRY(hs_run_csr_umma(ctx, rows_out, n_dense, ptr_dev, cols_dev, vals_dev, col_base, (double*)ctx->part.p, ldP,
-                           seg_stride, n_seg_umma, flags));
   const size_t slots_b = ((size_t)n_slots * 8 + 255) & ~(size_t)255;
   const size_t slots4_b = ((size_t)n_slots * 4 + 255) & ~(size_t)255;
   HS_TRY(hs_ensure(ctx, ctx->spmm_slots, 2 * slots_b + 2 * slots4_b));
@@ -863,6 +879,7 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   prm.seg_stride = seg_stride;
   prm.ldP = ldP;
   prm.flags = flags;
+  prm.run_if_flag = run_if;
 
 #define HS_SPMM_CASE(NVv, Kv, Wv) \
   if (n_sub <= 0) {} else \
@@ -880,7 +897,7 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
   const int np = perm ? n_perm : out_n_perm;
   const int64_t nsel = perm ? n_units : out_n_sel;
 #define HS_EPI(NA) \
-  k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_seg_all, seg_stride, n_rows, ldP, G, Q, np, nsel, flags, out_dev)
+  k_p64_epilogue<NA><<<eb, 256, 0, st>>>(prm.P64, n_seg_all, seg_stride, n_rows, ldP, G, Q, np, nsel, flags, run_if, out_dev)
   if (nacc <= 1) HS_EPI(1);
   else if (nacc <= 2) HS_EPI(2);
   else if (nacc <= 3) HS_EPI(3);
@@ -1070,16 +1087,28 @@ int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
                                                             small_max, (uint2*)ctx->perm_cols.p);
   HS_LAUNCH_CHECK(ctx);
   const int* flag = nullptr;
+  // the pairs are ascending by cell and in range: the tensor-core tile path takes them as they are (its slab-kernel
+  // fallback covers values beyond fp16's range)
   HS_TRY(hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
-                          /*allow_umma=*/false, &flag, ctx->perm_cols.p));
+                          /*allow_tiles=*/true, &flag, ctx->perm_cols.p, n_ids));
   return HS_OK;
 }
 
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
-                       const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev) {
+                       const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev,
+                       const int** fallback_flag_out) {
   const int64_t n_rows = n_sel * (int64_t)n_perm;
+  if (fallback_flag_out) *fallback_flag_out = nullptr;
   if (n_rows <= 0) return HS_OK;
-  const int S = hs_slab_cells(ctx);
+  int S = hs_slab_cells(ctx);
+  // Tile path: bucket by a power-of-two number of 64-cell slabs instead, so that the pairs are ordered at the
+  // granularity of the tile kernels' 4096-cell chunks (they need no order inside a chunk).
+  bool tiles = fallback_flag_out != nullptr && hs_tile_path_enabled(ctx) && (n_rows + 127) / 128 <= 65535;
+  if (tiles) {
+    int s2 = 64;
+    while (s2 < 4096 && ((ctx->N + s2 - 1) / s2 + 2) * 4 > 200 * 1024) s2 *= 2;
+    if (((ctx->N + s2 - 1) / s2 + 2) * 4 > 200 * 1024) tiles = false; else S = s2;
+  }
   if (S < 4) return -1;
   const int64_t n_slabs = (ctx->N + S - 1) / S;
   const int n_bins = (int)n_slabs + 1;                     // + overflow bin
@@ -1100,6 +1129,9 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
   k_perm_slab_sort<<<(unsigned)(n_rows * kSortMaxParts), kSortThreads, smem, st>>>(
       rp, gene_ptr_dev, n_perm, val_dev, ind_dev, index_base, ctx->N, magic, n_bins, part_items, (uint2*)ctx->perm_cols.p);
   HS_LAUNCH_CHECK(ctx);
+  if (tiles)      // ids outside [0, N) or values beyond fp16 raise *fallback_flag_out: the caller then gathers
+    return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
+                            /*allow_tiles=*/true, fallback_flag_out, ctx->perm_cols.p, n_ids, /*tile_only=*/true);
   return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
-                          /*allow_umma=*/false /* ids are only slab-sorted */, nullptr, ctx->perm_cols.p);
+                          /*allow_tiles=*/false /* ids are only slab-sorted */, nullptr, ctx->perm_cols.p);
 }

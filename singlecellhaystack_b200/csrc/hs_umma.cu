@@ -28,6 +28,7 @@
 #include <stdlib.h>
 
 #include "hs_common.cuh"
+#include "hs_ptx.cuh"
 
 namespace {
 
@@ -35,8 +36,6 @@ constexpr int kTileM = 128;          // rows (genes / permutations) per CTA
 constexpr int kTileN = 128;          // grid columns per CTA (G <= 128)
 constexpr int kBK = 64;              // cells per pipeline stage
 constexpr int kStagesDense = 3;   // dense / perm producers
-constexpr int kStagesCsr = 2;     // csr producer: the third stage's shared memory holds the entry rings
-constexpr int kRing = 64;         // csr: entries per row ring (>= cells per stage, so a stage never outruns it)
 constexpr int kTileBytes = kTileM * kBK * 2;          // 16 KB per fp16 operand term
 constexpr int kStageBytes = 4 * kTileBytes;           // A_hi, A_lo, B_hi, B_lo
 constexpr int kDrainBlocks = 1;      // TMEM -> registers after every stage (64 cells = 4 accumulating MMAs per sum)
@@ -47,84 +46,7 @@ constexpr float kScaleD = 16384.f;           // 2^14
 constexpr float kLoScale = 2048.f;           // 2^11
 constexpr uint32_t kLbo = 1024, kSbo = 2048;
 
-// ---- PTX wrappers ----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate, M = 128, N = 128, K = 16
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 16 consecutive fp32 columns of this thread's TMEM lane (no wait: the caller batches loads)
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+using namespace hs_ptx;
 
 // shared-memory matrix descriptor: MN-major, 128B swizzle, LBO / SBO as above, sm_100 version bit
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -197,8 +119,6 @@ struct UmmaParams {
   const float* v;          // perm: values [N]
   const int32_t* perm;     // perm: [N x n_rows] column-major
   int index_base;
-  // csr: tile row t is matrix row sorted_rows[t] (rows sorted by descending length)
-  const int32_t* sorted_rows;
   const int64_t* ptr;
   const int32_t* cols;
   const float* vals;
@@ -221,7 +141,7 @@ struct UmmaParams {
                            //        csr: column ids not ascending)
 };
 
-enum { kModeDense = 0, kModePerm = 1, kModeCsr = 2, kModeDenseTma = 3 };
+enum { kModeDense = 0, kModePerm = 1, kModeDenseTma = 3 };
 constexpr int kRawSlots = 3;                       // dense-tma: ring of raw fp32 tiles (64 cells x 128 rows)
 constexpr int kRawBytes = kBK * kTileM * 4;        // 32 KB
 
@@ -250,7 +170,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams p) {
   constexpr bool PERM = MODE == kModePerm;
   constexpr bool TMA = MODE == kModeDenseTma;
-  constexpr int kStages = (MODE == kModeCsr || TMA) ? 2 : kStagesDense;
+  constexpr int kStages = TMA ? 2 : kStagesDense;
   // dense mode uses the two otherwise idle warps (6, 7) as extra producers; dense-tma uses warp 6 as a
   // producer and warp 7 to stream raw fp32 tiles of E into a shared-memory ring with cp.async.bulk
   constexpr int kProducerWarps = MODE == kModeDense ? 6 : (TMA ? 5 : 4);
@@ -259,7 +179,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  const uint32_t ring_base = smem_u32(smem + kStages * kStageBytes + 256);   // csr mode: 2 x 32 KB entry rings
+  const uint32_t ring_base = smem_u32(smem + kStages * kStageBytes + 256);   // after stages + barriers
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto full_a = [&](int s) { return bar_base + 8u * s; };
@@ -269,7 +189,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   auto tmem_empty = [&](int b) { return bar_base + 8u * (3 * kStages + 2 + b); };
   auto raw_full = [&](int r) { return bar_base + 8u * (3 * kStages + 4 + r); };                 // dense-tma only
   auto raw_empty = [&](int r) { return bar_base + 8u * (3 * kStages + 4 + kRawSlots + r); };
-  const uint32_t raw_base = ring_base;   // same region as the csr rings: after stages + barriers
+  const uint32_t raw_base = ring_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // development aid: cycles each role spends blocked on each barrier (CTA (0,0) only)
@@ -336,139 +256,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
   } else if (warp < 4 || (MODE == kModeDense && (warp == 6 || warp == 7)) || (TMA && warp == 6)) {
     // ================= A producers =================
     bool over = false;
-    if (MODE == kModeCsr) {
-      // Scatter producer: thread r owns tile row r.  Rows are dense-ish (>= a few % non-zero), so the
-      // dense-equivalent MMA work beats gathering D rows per non-zero.  Each stage: the 8 threads of a
-      // row group zero its 16-byte chunks (8 cells each, hi and lo), then every thread walks its row's
-      // ascending (col, val) run and drops the split value into (row, cell).  Entries are fetched four
-      // at a time with the next four always in flight.
-      const int r = threadIdx.x, mg = r >> 3, sub = r & 7;
-      const int64_t trow = row0 + r;
-      const int rowid = trow < p.n_rows ? p.sorted_rows[trow] : -1;
-      int64_t pos = 0, end = 0;
-      if (rowid >= 0) {
-        pos = p.ptr[rowid];
-        end = p.ptr[rowid + 1];
-        const int64_t cb = kb_begin * kBK;
-        if (cb > 0) {   // first stored column >= segment start (rows are ascending)
-          int64_t lo = pos, hi = end;
-          while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if ((int64_t)p.cols[mid] - p.col_base < cb) lo = mid + 1; else hi = mid;
-          }
-          pos = lo;
-        }
-      }
-      // Per-thread ring of kRing (col, val) entries in shared memory, filled with 4-byte cp.async copies.
-      // All threads top their rings up at the same point (the start of a stage), eight commit groups
-      // each (empty ones included), so the copies issue as converged warp instructions and
-      // "wait_group 8" at the next stage start means "everything requested before this stage has landed".
-      // The lines a row will need ~256 entries ahead are prefetched into L2, so the cp.async copies see L2
-      // rather than HBM latency.
-      const uint32_t ring_c = ring_base + 4u * r;                      // slot stride 512 B (128 threads)
-      const uint32_t ring_v = ring_base + 128u * kRing * 4u + 4u * r;
-      const int64_t pos0 = pos;
-      int64_t head = pos, tail = pos, ready = pos, pf = pos;
-      bool violation = false;
-      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-      for (int i = 0; i < n_kb; ++i) {
-        // ---- L2 prefetch and ring top-up (converged) ----
-#pragma unroll 1
-        for (int it = 0; it < 4 && pf < end && pf < head + 320; ++it, pf += 32) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cols + pf));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vals + pf));
-        }
-        const int64_t prev_head = head;
-#pragma unroll
-        for (int g8 = 0; g8 < kRing / 8; ++g8) {
-          if (head - tail <= kRing - 8 && head < end) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (head + j < end) {
-                const uint32_t slot = (uint32_t)((head + j - pos0) & (kRing - 1)) * 512u;
-                cp_async4(ring_c + slot, p.cols + head + j);
-                cp_async4(ring_v + slot, p.vals + head + j);
-              }
-            head += 8;
-          }
-          cp_async_commit();
-        }
-        cp_async_wait<kRing / 8>();
-        ready = hs_min<int64_t>(prev_head, end);
-        const int s = i % kStages;
-        if (i >= kStages) mbar_wait(empty(s), ((i / kStages) - 1) & 1);
-        const uint32_t a_hi = smem_base + s * kStageBytes, a_lo = a_hi + kTileBytes;
-        const int64_t c0 = (kb_begin + i) * kBK;
-        const int c_hi = (int)hs_min<int64_t>(c0 + kBK, p.N);   // ids >= N are never consumed (-> NaN below)
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          const uint32_t off = chunk_off(mg, 8 * sub + kk);
-          sts_u4(a_hi + off, zero4);
-          sts_u4(a_lo + off, zero4);
-        }
-        __syncwarp();   // a row group's 8 threads are consecutive lanes
-        bool more = tail < end;
-        while (more) {
-          if (tail >= ready) {          // a row denser than the ring's lead: wait for what was just requested
-            if (tail >= head && head < end) {   // ring ran dry inside a stage (> 56 entries in 64 cells)
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (head + j < end) {
-                  const uint32_t slot = (uint32_t)((head + j - pos0) & (kRing - 1)) * 512u;
-                  cp_async4(ring_c + slot, p.cols + head + j);
-                  cp_async4(ring_v + slot, p.vals + head + j);
-                }
-              cp_async_commit();
-              head += 8;
-            }
-            cp_async_wait<0>();
-            ready = hs_min<int64_t>(head, end);
-          }
-          // up to four entries per trip: the ring reads are independent, the scatter is in order
-          int c[4];
-          float v[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint32_t slot = (uint32_t)((tail + j - pos0) & (kRing - 1)) * 512u;
-            c[j] = (tail + j < ready) ? (int)lds_u32(ring_c + slot) - p.col_base : 0x7fffffff;
-            v[j] = __uint_as_float(lds_u32(ring_v + slot));
-          }
-          int used = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (used == j && c[j] < c_hi) {
-              if (c[j] >= (int)c0) {
-                const float x = v[j] * kScaleA;
-                const __half h = __float2half_rn(x);
-                const float hf = __half2float(h);
-                over |= isinf(hf) && !isinf(x);
-                const __half l = __float2half_rn((x - hf) * kLoScale);
-                const uint32_t off = chunk_off(mg, c[j] - (int)c0) + 2u * sub;
-                sts_u16(a_hi + off, __half_as_ushort(h));
-                sts_u16(a_lo + off, __half_as_ushort(l));
-              } else {
-                violation = true;   // an id before this block: the row is not ascending (or negative)
-              }
-              used = j + 1;
-            }
-          }
-          tail += used;
-          // stop at the first entry of a later block; go on if the trip ended on the ring's ready edge
-          more = tail < end && (used == 4 || tail >= ready);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full_a(s));
-      }
-      cp_async_wait<0>();
-      // entries left after the last block of the last segment carry ids >= N: hand the call to the gather
-      // kernel, which poisons exactly those rows (an error path; speed is irrelevant)
-      if (rowid >= 0 && blockIdx.y == gridDim.y - 1 && tail < end) {
-        const int c = (int)lds_u32(ring_c + (uint32_t)((tail - pos0) & (kRing - 1)) * 512u) - p.col_base;
-        if (tail < head && c != 0x7fffffff) violation = true;
-      }
-      if (__any_sync(0xffffffffu, violation || over) && lane == 0) atomicOr(p.flags, 1);
-    } else
     for (int i = 0; i < n_kb; ++i) {
       const int s = i % kStages;
       if (i >= kStages) timed_wait(empty(s), ((i / kStages) - 1) & 1, 0);
@@ -635,7 +422,7 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
     // ================= epilogue: TMEM -> fp32 registers -> fp64 =================
     const int q = warp & 3, half = (warp - 8) >> 2;            // TMEM lane quarter, column half
     const int64_t trow = row0 + 32 * q + lane;
-    const int64_t row = (MODE == kModeCsr) ? (trow < p.n_rows ? (int64_t)p.sorted_rows[trow] : (int64_t)-1) : trow;
+    const int64_t row = trow;
     const int col0 = 64 * half;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
     float acc2[64];
@@ -694,7 +481,6 @@ __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams
 }
 
 constexpr size_t kUmmaSmem = 1024 + (size_t)kStagesDense * kStageBytes + 256;
-constexpr size_t kUmmaSmemCsr = 1024 + (size_t)kStagesCsr * kStageBytes + 256 + 2 * 128 * kRing * 4;
 constexpr size_t kUmmaSmemTma = 1024 + 2 * (size_t)kStageBytes + 256 + (size_t)kRawSlots * kRawBytes;
 
 template <int NACC>
@@ -721,7 +507,7 @@ k_p64_kl(const double* __restrict__ P64, int n_seg, int64_t seg_stride, int64_t 
 }  // namespace
 
 // (Re)build the pre-tiled fp16 density operands for the resident state.
-static int ensure_density_tiles(hs_ctx* ctx) {
+int hs_ensure_density_tiles(hs_ctx* ctx) {
   if (ctx->tiles_valid) return HS_OK;
   const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
   HS_TRY(hs_ensure(ctx, ctx->dtile_hi, (size_t)total_kb * kTileBytes));
@@ -742,7 +528,7 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
                       const int** flag_dev_out) {
   if (n_rows <= 0) return HS_OK;
   if (ctx->G > kTileN) return -1;
-  HS_TRY(ensure_density_tiles(ctx));
+  HS_TRY(hs_ensure_density_tiles(ctx));
   const int ldP = kTileN;
   HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
   cudaStream_t st = ctx->stream;
@@ -804,53 +590,3 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
   return HS_OK;
 }
 
-// cell segments the CSR tensor-core launch uses: about two waves of CTAs, at least 64 blocks per segment
-static void csr_umma_plan(const hs_ctx* ctx, int64_t n_dense, int64_t* kb_per_seg, int64_t* n_seg) {
-  const int row_tiles = (int)((n_dense + kTileM - 1) / kTileM);
-  const int64_t total_kb = (ctx->N + kBK - 1) / kBK;
-  int64_t ns = hs_max<int64_t>(1, (2 * (int64_t)ctx->sm_count + row_tiles - 1) / row_tiles);
-  ns = hs_min<int64_t>(ns, hs_max<int64_t>(1, total_kb / 64));
-  *kb_per_seg = (total_kb + ns - 1) / ns;
-  *n_seg = (total_kb + *kb_per_seg - 1) / *kb_per_seg;
-}
-
-int hs_csr_umma_segments(const hs_ctx* ctx, int64_t n_dense) {
-  int64_t kb = 0, ns = 0;
-  csr_umma_plan(ctx, n_dense, &kb, &ns);
-  return (int)ns;
-}
-
-// Tensor-core contraction of the n_dense densest CSR rows (tile row t = matrix row sorted_rows_dev[t]).
-// Adds into P64 ([n_seg][rows][ldP] fp64 column sums, zeroed by the caller); flags bit 0 requests the fallback.
-int hs_run_csr_umma(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_dense, const int64_t* ptr_dev,
-                    const int32_t* cols_dev, const float* vals_dev, int col_base, double* P64, int ldP,
-                    int64_t seg_stride, int n_seg_expected, int* flags) {
-  if (n_dense <= 0) return HS_OK;
-  if (ctx->G > kTileN) return hs_fail(ctx, HS_ERR_INVALID, "internal: tensor-core CSR path needs grid.points <= 128");
-  HS_TRY(ensure_density_tiles(ctx));
-  const int row_tiles = (int)((n_dense + kTileM - 1) / kTileM);
-  int64_t kb_per_seg = 0, n_seg = 0;
-  csr_umma_plan(ctx, n_dense, &kb_per_seg, &n_seg);
-  if (n_seg != n_seg_expected) return hs_fail(ctx, HS_ERR_INVALID, "internal: segment plan mismatch");
-  UmmaParams prm = {};
-  prm.sorted_rows = sorted_rows_dev;
-  prm.ptr = ptr_dev;
-  prm.cols = cols_dev;
-  prm.vals = vals_dev;
-  prm.col_base = col_base;
-  prm.n_rows = n_dense;
-  prm.N = ctx->N;
-  prm.Dh = (const unsigned char*)ctx->dtile_hi.p;
-  prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
-  prm.kblocks_per_seg = kb_per_seg;
-  prm.P64 = P64;
-  prm.seg_stride = seg_stride;
-  prm.ldP = ldP;
-  prm.G = ctx->G;
-  prm.flags = flags;
-  dim3 grid(row_tiles, (unsigned)n_seg);
-  HS_CUDA(ctx, cudaFuncSetAttribute(k_dense_umma<kModeCsr>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUmmaSmemCsr));
-  k_dense_umma<kModeCsr><<<grid, kUmmaThreads, kUmmaSmemCsr, ctx->stream>>>(prm);
-  HS_LAUNCH_CHECK(ctx);
-  return HS_OK;
-}

@@ -226,9 +226,17 @@ class DeviceContext:
         import torch.distributed as dist
         d_ptr, d_bytes, q_ptr, q_bytes = self.density_buffers(n_cells, n_grid)
         dev = torch.device("cuda", self.device)
+        # The collective runs on torch's stream, the library on the context's stream (its own
+        # non-blocking stream unless use_torch_stream() joined them): order the two explicitly.
+        # Before: everything the context has queued (the density stage on `src`, readers of the
+        # old state elsewhere) must have finished.  After: the context may not read D / Q /
+        # bandwidth until the broadcast has landed (NCCL calls return before they complete).
+        self.synchronize()
         for ptr, nbytes in ((d_ptr, d_bytes), (q_ptr, q_bytes)):
             t = _wrap_device_ptr(ptr, nbytes, dev)
             dist.broadcast(t, src=src, group=group)
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()
         if dist.get_rank(group) != src:
             self.density_commit(n_cells, n_grid)
 

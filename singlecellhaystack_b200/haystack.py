@@ -109,6 +109,12 @@ def select_genes_to_randomize(coeffVar, n_genes_to_randomize, method="heavytails
     if method == "uniform":
         pos = np.floor(_seq_length_out(1, count_genes, s)).astype(np.int64)
     elif method == "heavytails":
+        if s < 18 or count_genes < 18:
+            # R: seq(10, M - 9, length.out = S - 18) stops with "'length.out' must be a non-negative number"
+            # (R/haystack_continuous.R:233-235); fail as clearly instead of returning 18 (possibly repeated) rows
+            raise ValueError("'heavytails' selection needs at least 18 genes to randomize "
+                             f"(n.genes.to.randomize = {s}, genes = {count_genes}); use "
+                             "selection.method.genes.to.randomize = 'uniform'")
         mid = np.trunc(_seq_length_out(10, count_genes - 9, s - 18)).astype(np.int64)
         pos = np.concatenate([np.arange(1, 10), mid, count_genes - np.arange(8, -1, -1)])
     else:
@@ -177,7 +183,8 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         if x.ndim == 2 and x.shape[1] != grid_coord.shape[1]:
             raise ValueError("Coordinates and grid points have different number of columns.")
         xc, gc = getattr(x_in, "columns", None), getattr(grid_coord, "columns", None)
-        if (xc is not None or gc is not None) and list(xc or []) != list(gc or []):
+        if (xc is not None or gc is not None) and \
+                (list(xc) if xc is not None else []) != (list(gc) if gc is not None else []):
             raise ValueError("Coordinates and grid points have different column names.")
 
     # ---- expression container -------------------------------------------------------------
@@ -419,7 +426,8 @@ def haystack(x, expression=None, *, coord=None, assay=None, slot="data", dims=No
         emb = np.asarray(x.obsm[coord], dtype=np.float64)
         if dims is not None:
             emb = emb[:, list(dims)]
-        names = list(getattr(getattr(x, "var_names", None), "values", getattr(x, "var_names", None)) or []) or None
+        vn = getattr(x, "var_names", None)
+        names = list(vn) if vn is not None and len(vn) else None
         import scipy.sparse as sp
         expr = _sparse.as_RsparseMatrix(sp.csr_matrix(mat).T.tocsr()) if sp.issparse(mat) else np.asarray(mat).T
         return haystack(emb, expr, weights_advanced_Q=weights_advanced_Q, dir_randomization=dir_randomization,

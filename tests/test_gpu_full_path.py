@@ -151,8 +151,10 @@ def test_density_buffers_roundtrip(ctx, toy):
         np.testing.assert_array_equal(other.dkl_csr(sp_.p, sp_.j, sp_.x), want)
 
 
-def test_tensor_core_csr_rows_opt_in(ctx, monkeypatch):
-    """HS_UMMA_MIN_DENSITY routes the densest CSR rows through the tcgen05 scatter producer; same tolerance."""
+def test_tile_path_is_the_default_csr_path(monkeypatch):
+    """The CSR contraction runs on the tensor-core tile kernels by default (csrc/hs_tiles.cu); HS_TILE_DISABLE=1
+    selects the SIMT slab kernel.  Same tolerance, different summation order."""
+    from singlecellhaystack_b200.device import DeviceContext
     n, d, g, m = 20000, 10, 100, 600
     x, labels = synth.make_embedding(n, d)
     xs, _, _ = synth.scale_coords(x)
@@ -160,12 +162,17 @@ def test_tensor_core_csr_rows_opt_in(ctx, monkeypatch):
     p, j, v = synth.make_csr_numpy(m, n, 0.15, labels)
     ref = ho.density_stage(xs, grid)
     want = ho.dkl_observed(ho.RowSparse(p=p, j=j, x=v, shape=(m, n)), ref["density"], ref["Q"])
-    ctx.density(xs, grid)
-    base = ctx.dkl_csr(p, j, v)
-    monkeypatch.setenv("HS_UMMA_MIN_DENSITY", "0.04")
-    got = ctx.dkl_csr(p, j, v)
-    assert _rel(base, want) < RTOL_DKL and _rel(got, want) < RTOL_DKL
-    assert not np.array_equal(got, base)          # the densest rows really took the other path
+    res = {}
+    for name in ("tiles", "slab"):
+        if name == "slab":
+            monkeypatch.setenv("HS_TILE_DISABLE", "1")
+        else:
+            monkeypatch.delenv("HS_TILE_DISABLE", raising=False)
+        with DeviceContext(0) as c:
+            c.density(xs, grid)
+            res[name] = c.dkl_csr(p, j, v)
+    assert _rel(res["tiles"], want) < RTOL_DKL and _rel(res["slab"], want) < RTOL_DKL
+    assert not np.array_equal(res["tiles"], res["slab"])          # two different kernels really ran
 
 
 def test_front_door_dispatch_variants(ctx, toy, tmp_path):
