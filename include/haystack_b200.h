@@ -89,6 +89,23 @@ int hs_density_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, void** d_dev, i
                        void** q_dev, int64_t* q_bytes);
 /* Declare the buffers filled: reads the bandwidth back from q_dev[n_grid] and validates it. */
 int hs_density_commit(hs_ctx* ctx, int64_t n_cells, int n_grid);
+/* The same exchange with the CELLS sharded instead (R/haystack_continuous.R:168-186 is per cell but for one scalar,
+ * the bandwidth = median over all cells of the distance to the nearest grid point): rank r of `world` computes the
+ * squared distances and row minima of its cell range (hs_density_shard_dist_dev), the host layer all-gathers the row
+ * minima in place, every rank takes the exact median of all of them and fills the density rows and per-block column
+ * sums of its range (hs_density_shard_dens_dev), those are all-gathered in place too, and hs_density_shard_finish
+ * reduces Q in the fixed order of the single-GPU path -- so every rank ends with the bits hs_density_dev would have
+ * produced, and no rank computes more than 1/world of the stage.  Ranges are whole 128-cell blocks;
+ * hs_density_shard_buffers reports the three device buffers and the bytes each rank contributes (rank r's part starts
+ * at r * bytes_per_rank), to be called after hs_density_shard_dist_dev. */
+int hs_density_shard_dist_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims,
+                              const double* grid_dev, int n_grid, int rank, int world);
+int hs_density_shard_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, int world, void** rowmin_dev,
+                             int64_t* rowmin_bytes_per_rank, void** d_dev, int64_t* d_bytes_per_rank,
+                             void** qpart_dev, int64_t* qpart_bytes_per_rank);
+int hs_density_shard_dens_dev(hs_ctx* ctx, int64_t n_cells, int n_grid, const double* w_q_dev, int rank,
+                              int world);
+int hs_density_shard_finish(hs_ctx* ctx, int64_t n_cells, int n_grid, double* bandwidth_out, double* q_out);
 /* Shape of the resident state (0,0 when none). */
 int hs_density_shape(const hs_ctx* ctx, int64_t* n_cells_out, int* n_grid_out);
 
@@ -165,6 +182,12 @@ int hs_dkl_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, cons
 int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,
                                const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base,
                                double* out_dev);
+/* The same for units whose streams the caller names: unit u, randomization r draws from stream
+ * unit_stream_dev[u] + r.  Lets several ranks split the (gene, permutation block) units of one job and still draw
+ * exactly what a single rank would (stream of gene s, randomization r = s * n_perm_total + r). */
+int hs_dkl_perm_csr_seeded_units_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_units,
+                                     const float* val_dev, int n_perm, uint64_t seed,
+                                     const uint64_t* unit_stream_dev, double* out_dev);
 int hs_dkl_perm_dense_seeded_dev(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed,
                                  uint64_t stream_base, double* out_dev);
 int hs_dkl_perm_csr_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel,

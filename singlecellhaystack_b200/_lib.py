@@ -45,6 +45,12 @@ SIGNATURES = {
     "hs_dkl_csr_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "hs_dkl_perm_csr_seeded_dev": (_int, [_vp, _vp, _i64, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
     "hs_dkl_perm_csr_dev": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
+    "hs_dkl_perm_csr_seeded_units_dev": (_int, [_vp, _vp, _i64, _vp, _int, C.c_uint64, _vp, _vp]),
+    "hs_density_shard_dist_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _int, _int]),
+    "hs_density_shard_buffers": (_int, [_vp, _i64, _int, _int, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp),
+                                        C.POINTER(_i64), C.POINTER(_vp), C.POINTER(_i64)]),
+    "hs_density_shard_dens_dev": (_int, [_vp, _i64, _int, _vp, _int, _int]),
+    "hs_density_shard_finish": (_int, [_vp, _i64, _int, _vp, _vp]),
     "hs_dkl_dense_dev": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_dkl_perm_dense_dev": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "hs_density_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),

@@ -850,6 +850,94 @@ int hs_dkl_perm_csr_seeded_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t
   } HS_ABI_CATCH(ctx)
 }
 
+int hs_dkl_perm_csr_seeded_units_dev(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_units, const float* val_dev,
+                                     int n_perm, uint64_t seed, const uint64_t* unit_stream_dev, double* out_dev) {
+  try {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_units < 0 || n_perm <= 0 || !gene_ptr_dev || !out_dev || (n_units > 0 && !unit_stream_dev))
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded_units_dev: bad arguments");
+  if (n_units == 0) return HS_OK;
+  int64_t n_vals = 0;
+  HS_CUDA(ctx, cudaMemcpyAsync(&n_vals, gene_ptr_dev + n_units, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_vals < 0) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded_units_dev: gene_ptr is not a prefix sum");
+  if (n_vals > 0 && !val_dev) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_seeded_units_dev: val is NULL");
+  ScopedTimer tm(ctx, HS_T_PERM);
+  HS_TRY(hs_run_perm_seeded(ctx, gene_ptr_dev, n_units, n_vals, val_dev, n_perm, seed, 0, out_dev,
+                            (const unsigned long long*)unit_stream_dev));
+  tm.stop();
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+// ---- density stage with the cells sharded over ranks ----
+static int shard_range(hs_ctx* ctx, int64_t n_cells, int rank, int world, int64_t* lo, int64_t* hi) {
+  if (world < 1 || rank < 0 || rank >= world) return hs_fail(ctx, HS_ERR_INVALID, "bad rank / world");
+  const int64_t per = hs_density_cells_per_rank(n_cells, world);
+  *lo = hs_min<int64_t>(n_cells, (int64_t)rank * per);
+  *hi = hs_min<int64_t>(n_cells, *lo + per);
+  return HS_OK;
+}
+
+int hs_density_shard_dist_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims, const double* grid_dev,
+                              int n_grid, int rank, int world) {
+  try {
+  HS_TRY(check_density_args(ctx, x_dev, n_cells, n_dims, grid_dev, n_grid));
+  HS_TRY(set_device(ctx));
+  int64_t lo = 0, hi = 0;
+  HS_TRY(shard_range(ctx, n_cells, rank, world, &lo, &hi));
+  ctx->N = 0;
+  return hs_density_step_dist(ctx, x_dev, n_cells, n_dims, grid_dev, n_grid, lo, hi, world);
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_density_shard_buffers(hs_ctx* ctx, int64_t n_cells, int n_grid, int world, void** rowmin_dev,
+                             int64_t* rowmin_bytes_per_rank, void** d_dev, int64_t* d_bytes_per_rank, void** qpart_dev,
+                             int64_t* qpart_bytes_per_rank) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  if (n_cells <= 0 || n_grid <= 0 || world < 1 || !ctx->rowmin.p || !ctx->D32.p || !ctx->qpart.p)
+    return hs_fail(ctx, HS_ERR_STATE, "hs_density_shard_buffers: call hs_density_shard_dist_dev first");
+  const int64_t per = hs_density_cells_per_rank(n_cells, world);
+  const int ldD = hs_ld_for_grid(n_grid);
+  if (rowmin_dev) *rowmin_dev = ctx->rowmin.p;
+  if (d_dev) *d_dev = ctx->D32.p;
+  if (qpart_dev) *qpart_dev = ctx->qpart.p;
+  if (rowmin_bytes_per_rank) *rowmin_bytes_per_rank = (int64_t)sizeof(double) * per;
+  if (d_bytes_per_rank) *d_bytes_per_rank = (int64_t)sizeof(float) * per * ldD;
+  if (qpart_bytes_per_rank) *qpart_bytes_per_rank = (int64_t)sizeof(double) * (per / 128) * n_grid;
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_density_shard_dens_dev(hs_ctx* ctx, int64_t n_cells, int n_grid, const double* w_q_dev, int rank, int world) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  int64_t lo = 0, hi = 0;
+  HS_TRY(shard_range(ctx, n_cells, rank, world, &lo, &hi));
+  return hs_density_step_dens(ctx, n_cells, n_grid, w_q_dev, lo, hi, false);
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_density_shard_finish(hs_ctx* ctx, int64_t n_cells, int n_grid, double* bandwidth_out, double* q_out) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  HS_TRY(hs_density_step_q(ctx, n_cells, n_grid));
+  cudaStream_t st = ctx->stream;
+  if (q_out) HS_CUDA(ctx, cudaMemcpyAsync(q_out, ctx->Q.p, sizeof(double) * n_grid, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (bandwidth_out) *bandwidth_out = ctx->bw;
+  if (!(ctx->bw > 0.0)) {
+    ctx->N = 0;
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_density_shard_finish: bandwidth %g is not positive", ctx->bw);
+  }
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
 int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, int n_perm,
                            uint64_t seed, uint64_t stream_base, double* out) {
   try {

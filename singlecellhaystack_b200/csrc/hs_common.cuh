@@ -144,7 +144,15 @@ int hs_run_row_stats_f32(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, 
 int hs_run_perm_dense_seeded(hs_ctx* ctx, const float* v_dev, int n_perm, uint64_t seed, uint64_t stream_base,
                              double* out_dev);
 int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
-                       const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev);
+                       const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev,
+                       const unsigned long long* unit_stream_dev = nullptr);
+// density stage in shardable steps (hs_density.cu)
+int hs_density_step_dist(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
+                         int64_t c_lo, int64_t c_hi, int world);
+int hs_density_step_dens(hs_ctx* ctx, int64_t N, int G, const double* wq_dev, int64_t c_lo, int64_t c_hi,
+                         bool want_dens64);
+int hs_density_step_q(hs_ctx* ctx, int64_t N, int G);
+int64_t hs_density_cells_per_rank(int64_t N, int world);
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev,
                int64_t n_rows, double* out_dev);
 int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,

@@ -19,11 +19,14 @@ constexpr int kJT = 4;  // grid points per register tile in the distance kernel
 // dist.to.grid) so that both the write here and the read in k_density are coalesced over cells.
 __global__ void __launch_bounds__(kCellsPerBlock)
 k_sqdist(const double* __restrict__ x, int64_t N, int d, const double* __restrict__ grid, int G,
-         int jchunk, double* __restrict__ sq, double* __restrict__ rowmin, int32_t* __restrict__ nearest) {
+         int jchunk, int64_t c_lo, int64_t c_hi, double* __restrict__ sq, double* __restrict__ rowmin,
+         int32_t* __restrict__ nearest) {
+  // cells [c_lo, c_hi) of the N x d matrix; sq holds only this range, [G][c_hi - c_lo]
   extern __shared__ double gs[];  // [jchunk][d]
-  const int64_t c = (int64_t)blockIdx.x * kCellsPerBlock + threadIdx.x;
-  const bool valid = c < N;
-  const int64_t cc = valid ? c : N - 1;
+  const int64_t c = c_lo + (int64_t)blockIdx.x * kCellsPerBlock + threadIdx.x;
+  const bool valid = c < c_hi;
+  const int64_t cc = valid ? c : c_hi - 1;
+  const int64_t n_loc = c_hi - c_lo;
   double best = INFINITY;
   int bestj = 0;
   for (int j0 = 0; j0 < G; j0 += jchunk) {
@@ -54,7 +57,7 @@ k_sqdist(const double* __restrict__ x, int64_t N, int d, const double* __restric
       for (int t = 0; t < kJT; ++t) {
         if (jj + t < jn) {
           const int j = j0 + jj + t;
-          if (valid) sq[(int64_t)j * N + c] = s[t];
+          if (valid) sq[(int64_t)j * n_loc + (c - c_lo)] = s[t];
           if (s[t] < best) {  // strict: first minimum wins
             best = s[t];
             bestj = j;
@@ -133,15 +136,17 @@ __global__ void k_sel_final(const SelState* st, double* bw) {
 
 // ---- density + per-block column sums ------------------------------------------------------------
 __global__ void __launch_bounds__(kCellsPerBlock)
-k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, const double* __restrict__ bw_dev,
-          const double* __restrict__ wq, float* __restrict__ D32, double* __restrict__ dens64,
-          double* __restrict__ qpart) {
+k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, int64_t c_lo, int64_t c_hi,
+          const double* __restrict__ bw_dev, const double* __restrict__ wq, float* __restrict__ D32,
+          double* __restrict__ dens64, double* __restrict__ qpart) {
   extern __shared__ unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);                               // [128][129]
   double* qs = reinterpret_cast<double*>(smem_raw + sizeof(float) * 128 * 129 + 8); // [4][128]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t c = (int64_t)blockIdx.x * kCellsPerBlock + tid;
-  const bool valid = c < N;
+  const int64_t c = c_lo + (int64_t)blockIdx.x * kCellsPerBlock + tid;
+  const bool valid = c < c_hi;
+  const int64_t n_loc = c_hi - c_lo;
+  const int64_t gblock = c_lo / kCellsPerBlock + blockIdx.x;      // block number among all cells
   const double bw = *bw_dev;
   const double w = (valid && wq) ? wq[c] : 1.0;
   for (int j0 = 0; j0 < ldD; j0 += 128) {
@@ -150,7 +155,7 @@ k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, const double
     for (int jj = 0; jj < jn; ++jj) {
       double dv = 0.0;
       if (valid) {
-        const double dist = sqrt(sq[(int64_t)(j0 + jj) * N + c]);
+        const double dist = sqrt(sq[(int64_t)(j0 + jj) * n_loc + (c - c_lo)]);
         const double dn = dist / bw;                // :175
         dv = exp(-dn * dn / 2);                     // :176-177
         if (dens64) dens64[(int64_t)(j0 + jj) * N + c] = dv;
@@ -162,10 +167,10 @@ k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, const double
     for (int jj = jn; jj < jpad; ++jj) tile[tid * 129 + jj] = 0.f;
     __syncthreads();
     for (int jj = tid; jj < jn; jj += kCellsPerBlock)
-      qpart[(int64_t)blockIdx.x * G + j0 + jj] = (qs[jj] + qs[128 + jj]) + (qs[256 + jj] + qs[384 + jj]);
+      qpart[gblock * G + j0 + jj] = (qs[jj] + qs[128 + jj]) + (qs[256 + jj] + qs[384 + jj]);
     for (int r = warp; r < kCellsPerBlock; r += 4) {
-      const int64_t cr = (int64_t)blockIdx.x * kCellsPerBlock + r;
-      if (cr < N)
+      const int64_t cr = c_lo + (int64_t)blockIdx.x * kCellsPerBlock + r;
+      if (cr < c_hi)
         for (int jj = lane; jj < jpad; jj += 32) D32[cr * ldD + j0 + jj] = tile[r * 129 + jj];
     }
     __syncthreads();
@@ -220,30 +225,51 @@ int hs_run_f64_to_f32(hs_ctx* ctx, const double* src, float* dst, int64_t n, cud
   return HS_OK;
 }
 
-int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
-                   const double* wq_dev, bool want_dens64) {
-  const int ldD = hs_ld_for_grid(G);
-  const int nblocks = (int)((N + kCellsPerBlock - 1) / kCellsPerBlock);
-  HS_TRY(hs_ensure(ctx, ctx->sq, sizeof(double) * (size_t)N * G));
-  HS_TRY(hs_ensure(ctx, ctx->rowmin, sizeof(double) * (size_t)N));
-  HS_TRY(hs_ensure(ctx, ctx->nearest, sizeof(int32_t) * (size_t)N));
-  HS_TRY(hs_ensure(ctx, ctx->sel, sizeof(SelState) + 64));
-  HS_TRY(hs_ensure(ctx, ctx->qpart, sizeof(double) * (size_t)nblocks * G));
-  HS_TRY(hs_ensure(ctx, ctx->D32, sizeof(float) * (size_t)N * ldD));
-  HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)G + 64));
-  if (want_dens64) HS_TRY(hs_ensure(ctx, ctx->dens64, sizeof(double) * (size_t)N * G));
-  cudaStream_t st = ctx->stream;
+// The density stage in three steps, so that the cells can be sharded over ranks (one process per GPU): every rank
+// runs steps 1 and 2 on its own cell range [c_lo, c_hi) (whole 128-cell blocks) and the host layer all-gathers the
+// row minima after step 1 and the density rows + per-block column sums after step 2.  Every rank then holds exactly
+// the buffers a single-GPU run would hold, and step 3 (fixed-order reductions) gives the same bits everywhere.
+//   step 1  hs_density_step_dist:   squared distances, row minima and nearest grid point of [c_lo, c_hi)
+//   step 2  hs_density_step_dens:   exact median of ALL row minima -> bandwidth; density rows + column sums of [c_lo, c_hi)
+//   step 3  hs_density_step_q:      Q from all blocks' column sums; state becomes valid
+int64_t hs_density_cells_per_rank(int64_t N, int world) {
+  return ((N + world - 1) / world + kCellsPerBlock - 1) / kCellsPerBlock * kCellsPerBlock;
+}
+static int64_t padded_cells(int64_t N, int world) { return hs_density_cells_per_rank(N, world) * world; }
 
+int hs_density_step_dist(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
+                         int64_t c_lo, int64_t c_hi, int world) {
+  const int ldD = hs_ld_for_grid(G);
+  const int64_t Npad = padded_cells(N, world);
+  const int64_t n_loc = hs_max<int64_t>(c_hi - c_lo, 0);
+  const int nblocks_all = (int)(Npad / kCellsPerBlock);
+  HS_TRY(hs_ensure(ctx, ctx->sq, sizeof(double) * (size_t)hs_max<int64_t>(n_loc, 1) * G));
+  HS_TRY(hs_ensure(ctx, ctx->rowmin, sizeof(double) * (size_t)Npad));
+  HS_TRY(hs_ensure(ctx, ctx->nearest, sizeof(int32_t) * (size_t)Npad));
+  HS_TRY(hs_ensure(ctx, ctx->sel, sizeof(SelState) + 64));
+  HS_TRY(hs_ensure(ctx, ctx->qpart, sizeof(double) * (size_t)nblocks_all * G));
+  HS_TRY(hs_ensure(ctx, ctx->D32, sizeof(float) * (size_t)Npad * ldD));
+  HS_TRY(hs_ensure(ctx, ctx->Q, sizeof(double) * (size_t)G + 64));
+  if (n_loc <= 0) return HS_OK;
+  if (c_lo % kCellsPerBlock) return hs_fail(ctx, HS_ERR_INVALID, "internal: cell range must start on a 128-cell block");
+  cudaStream_t st = ctx->stream;
   // grid chunk staged in shared memory: <= 64 KB
   int jchunk = (int)hs_min<int64_t>(G, hs_max<int64_t>(kJT, (64 * 1024) / (sizeof(double) * (size_t)d)));
   const size_t smem1 = sizeof(double) * (size_t)jchunk * d;
   if (smem1 > 200 * 1024) return hs_fail(ctx, HS_ERR_INVALID, "n_dims=%d too large for the distance kernel", d);
   HS_CUDA(ctx, cudaFuncSetAttribute(k_sqdist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  k_sqdist<<<nblocks, kCellsPerBlock, smem1, st>>>(x_dev, N, d, grid_dev, G, jchunk, (double*)ctx->sq.p,
-                                                    (double*)ctx->rowmin.p, (int32_t*)ctx->nearest.p);
+  const int nb = (int)((n_loc + kCellsPerBlock - 1) / kCellsPerBlock);
+  k_sqdist<<<nb, kCellsPerBlock, smem1, st>>>(x_dev, N, d, grid_dev, G, jchunk, c_lo, c_hi, (double*)ctx->sq.p,
+                                               (double*)ctx->rowmin.p, (int32_t*)ctx->nearest.p);
   HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
 
-  // exact median of the row minima
+int hs_density_step_dens(hs_ctx* ctx, int64_t N, int G, const double* wq_dev, int64_t c_lo, int64_t c_hi,
+                         bool want_dens64) {
+  const int ldD = hs_ld_for_grid(G);
+  cudaStream_t st = ctx->stream;
+  // exact median of the row minima of all cells
   SelState* sel = (SelState*)ctx->sel.p;
   double* bw_dev = (double*)((char*)ctx->sel.p + sizeof(SelState));
   const long long ra = (N - 1) / 2, rb = N / 2;
@@ -258,25 +284,41 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
   }
   k_sel_final<<<1, 1, 0, st>>>(sel, bw_dev);
   HS_LAUNCH_CHECK(ctx);
+  const int64_t n_loc = hs_max<int64_t>(c_hi - c_lo, 0);
+  if (want_dens64) HS_TRY(hs_ensure(ctx, ctx->dens64, sizeof(double) * (size_t)N * G));
+  if (n_loc > 0) {
+    const size_t smem2 = sizeof(float) * 128 * 129 + 8 + sizeof(double) * 4 * 128;
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    const int nb = (int)((n_loc + kCellsPerBlock - 1) / kCellsPerBlock);
+    k_density<<<nb, kCellsPerBlock, smem2, st>>>((const double*)ctx->sq.p, N, G, ldD, c_lo, c_hi, bw_dev, wq_dev,
+                                                  (float*)ctx->D32.p, want_dens64 ? (double*)ctx->dens64.p : nullptr,
+                                                  (double*)ctx->qpart.p);
+    HS_LAUNCH_CHECK(ctx);
+  }
+  return HS_OK;
+}
 
-  const size_t smem2 = sizeof(float) * 128 * 129 + 8 + sizeof(double) * 4 * 128;
-  HS_CUDA(ctx, cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  k_density<<<nblocks, kCellsPerBlock, smem2, st>>>((const double*)ctx->sq.p, N, G, ldD, bw_dev, wq_dev,
-                                                     (float*)ctx->D32.p,
-                                                     want_dens64 ? (double*)ctx->dens64.p : nullptr,
-                                                     (double*)ctx->qpart.p);
-  HS_LAUNCH_CHECK(ctx);
+int hs_density_step_q(hs_ctx* ctx, int64_t N, int G) {
+  cudaStream_t st = ctx->stream;
+  const int nblocks = (int)((N + kCellsPerBlock - 1) / kCellsPerBlock);
+  double* bw_dev = (double*)((char*)ctx->sel.p + sizeof(SelState));
   k_q_colsum<<<G, 256, 0, st>>>((const double*)ctx->qpart.p, nblocks, G, (double*)ctx->Q.p);
   HS_LAUNCH_CHECK(ctx);
   k_q_finalize<<<1, 256, 0, st>>>(G, (double*)ctx->Q.p);
   HS_LAUNCH_CHECK(ctx);
-
   // the bandwidth rides behind Q so that one collective moves both (hs_density_buffers)
   HS_CUDA(ctx, cudaMemcpyAsync((double*)ctx->Q.p + G, bw_dev, sizeof(double), cudaMemcpyDeviceToDevice, st));
   HS_CUDA(ctx, cudaMemcpyAsync(&ctx->bw, bw_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
   ctx->N = N;
   ctx->G = G;
-  ctx->ldD = ldD;
+  ctx->ldD = hs_ld_for_grid(G);
   ctx->tiles_valid = false;
   return HS_OK;
+}
+
+int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
+                   const double* wq_dev, bool want_dens64) {
+  HS_TRY(hs_density_step_dist(ctx, x_dev, N, d, grid_dev, G, 0, N, 1));
+  HS_TRY(hs_density_step_dens(ctx, N, G, wq_dev, 0, N, want_dens64));
+  return hs_density_step_q(ctx, N, G);
 }

@@ -925,7 +925,8 @@ constexpr int kGenPerThread = 8;
 
 __global__ void __launch_bounds__(kGenThreads)
 k_perm_generate(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
-                const float* __restrict__ val, int64_t N, uint64_t seed, uint64_t stream_base, int small_max,
+                const float* __restrict__ val, int64_t N, uint64_t seed, uint64_t stream_base,
+                const unsigned long long* __restrict__ unit_stream, int small_max,
                 uint2* __restrict__ out) {
   __shared__ unsigned int s_warp[kGenThreads / 32];
   __shared__ unsigned int s_total, s_cnt;
@@ -936,7 +937,10 @@ k_perm_generate(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, 
   const int64_t g0 = gp[s];
   const uint32_t nnz = (uint32_t)(gp[s + 1] - g0);
   if (nnz <= (uint32_t)small_max) return;   // empty, or drawn forward by k_perm_generate_small
-  const HsPrp prp = hs_prp_make(seed, stream_base + (uint64_t)row, (uint32_t)N);
+  // stream of (unit s, randomization r): stream_base + s * n_perm + r, or unit_stream[s] + r when the caller names
+  // the units' streams (units dealt to ranks keep the streams of the whole job)
+  const uint64_t stream = unit_stream ? (uint64_t)unit_stream[s] + (uint64_t)(row - s * n_perm) : stream_base + (uint64_t)row;
+  const HsPrp prp = hs_prp_make(seed, stream, (uint32_t)N);
   uint2* dst = out + rp[row];
   const float* v = val + g0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1029,6 +1033,7 @@ using SmallSort = cub::BlockRadixSort<uint32_t, kSmallThreads, kSmallItems, uint
 __global__ void __launch_bounds__(kSmallThreads)
 k_perm_generate_small(const int64_t* __restrict__ rp, const int64_t* __restrict__ gp, int n_perm,
                       const float* __restrict__ val, int64_t N, uint64_t seed, uint64_t stream_base,
+                      const unsigned long long* __restrict__ unit_stream,
                       uint2* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char sort_smem[];
   SmallSort::TempStorage& tmp = *reinterpret_cast<SmallSort::TempStorage*>(sort_smem);
@@ -1038,7 +1043,10 @@ k_perm_generate_small(const int64_t* __restrict__ rp, const int64_t* __restrict_
   const int64_t nnz64 = gp[s + 1] - g0;
   if (nnz64 == 0 || nnz64 > kSmallRowMax) return;
   const uint32_t nnz = (uint32_t)nnz64;
-  const HsPrp prp = hs_prp_make(seed, stream_base + (uint64_t)row, (uint32_t)N);
+  // stream of (unit s, randomization r): stream_base + s * n_perm + r, or unit_stream[s] + r when the caller names
+  // the units' streams (units dealt to ranks keep the streams of the whole job)
+  const uint64_t stream = unit_stream ? (uint64_t)unit_stream[s] + (uint64_t)(row - s * n_perm) : stream_base + (uint64_t)row;
+  const HsPrp prp = hs_prp_make(seed, stream, (uint32_t)N);
   uint32_t keys[kSmallItems], vals[kSmallItems];
 #pragma unroll
   for (int k = 0; k < kSmallItems; ++k) {
@@ -1060,7 +1068,8 @@ k_perm_generate_small(const int64_t* __restrict__ rp, const int64_t* __restrict_
 }
 
 int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
-                       const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev) {
+                       const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev,
+                       const unsigned long long* unit_stream_dev) {
   const int64_t n_rows = n_sel * (int64_t)n_perm;
   if (n_rows <= 0) return HS_OK;
   if (n_rows > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "too many randomized rows in one call");
@@ -1080,11 +1089,11 @@ int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
     const size_t sm = sizeof(SmallSort::TempStorage);
     HS_CUDA(ctx, cudaFuncSetAttribute(k_perm_generate_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_perm_generate_small<<<(unsigned)n_rows, kSmallThreads, sm, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ctx->N, seed,
-                                                                     stream_base, (uint2*)ctx->perm_cols.p);
+                                                                     stream_base, unit_stream_dev, (uint2*)ctx->perm_cols.p);
     HS_LAUNCH_CHECK(ctx);
   }
   k_perm_generate<<<(unsigned)n_rows, kGenThreads, 0, st>>>(rp, gene_ptr_dev, n_perm, val_dev, ctx->N, seed, stream_base,
-                                                            small_max, (uint2*)ctx->perm_cols.p);
+                                                            unit_stream_dev, small_max, (uint2*)ctx->perm_cols.p);
   HS_LAUNCH_CHECK(ctx);
   const int* flag = nullptr;
   // the pairs are ascending by cell and in range: the tensor-core tile path takes them as they are (its slab-kernel

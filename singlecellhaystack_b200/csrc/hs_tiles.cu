@@ -59,7 +59,10 @@ constexpr int kEntryLookahead = 64 * 1024;       // bytes of a tile row's entry 
 constexpr int kBLookahead = 4;                   // density operand stages prefetched into L2
 constexpr int kFlushStages = 32;                 // fp32 registers -> fp64 every 32 stages (2048 cells)
 constexpr int kMmaThreads = 640;                 // 20 warps: 96 registers per thread (warps are allocated in fours)
-constexpr int kEpiWarp0 = 4;
+constexpr int kEpiWarps = 16;                    // warps 0..15 drain TMEM (TMEM lane quarter = warp % 4)
+constexpr int kLoaderWarp = 16, kProducerWarp0 = 17, kMmaWarp = 19;
+// The warp scheduler favours high warp ids: the MMA issuer, the producers and the loader sit above the sixteen
+// epilogue warps, or their few instructions queue behind the epilogue's polling and arithmetic.
 constexpr float kScaleD = 16384.f;               // must match hs_umma.cu (k_density_tiles)
 constexpr float kLoScale = 2048.f;
 constexpr uint32_t kLbo = 1024, kSbo = 2048;
@@ -173,9 +176,24 @@ k_tile_scan(const unsigned long long* __restrict__ cap, int64_t n, unsigned long
   if (threadIdx.x == 0) base[n] = carry;
 }
 
+// Lanes holding equal slab ids in a row (ids ascend along a row run, so equal ids are neighbours; if they are not,
+// a slab simply gets several runs): head lane and length of this lane's run.  Cheaper than __match_any_sync.
+__device__ __forceinline__ void lane_run(int s, int lane, int& head, int& len) {
+  const int prev = __shfl_up_sync(0xffffffffu, s, 1);
+  const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || s != prev);
+  head = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const unsigned after = lane == 31 ? 0u : (heads >> (lane + 1)) << (lane + 1);
+  const int next = after ? __ffs(after) - 1 : 32;
+  len = next - head;
+}
+
 // ---- step 1d: fill the regions ----------------------------------------------------------------------------------------
+// Instruction-lean on purpose (the first version spent 5.6 warp instructions per entry and was issue-bound at
+// 73 % issue utilisation, profiles/r2_tile_fill_v1_raw.csv): 32-bit cell arithmetic, the source layout a template
+// parameter, the row part of the operand offset hoisted, run detection by shuffle + ballot instead of match.
 constexpr int kFillThreads = 512;
 
+template <bool PAIRS>
 __global__ void __launch_bounds__(kFillThreads)
 k_tile_fill(const TileSrc src, const int32_t* __restrict__ sorted_rows, int64_t n_rows, int64_t N, int n_chunks,
             int n_slabs, const uint32_t* __restrict__ cuts, const unsigned long long* __restrict__ region_base,
@@ -187,8 +205,10 @@ k_tile_fill(const TileSrc src, const int32_t* __restrict__ sorted_rows, int64_t 
   __shared__ uint32_t row_a[kTM], row_b[kTM];
   const int c = blockIdx.x, t = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t cell0 = (int64_t)c * kChunkCells;
-  const int64_t cell1 = hs_min<int64_t>(N, cell0 + kChunkCells);
+  // cell ids relative to the chunk, as unsigned: anything outside [0, n_cell) -- ids before the chunk included --
+  // compares as too large
+  const int32_t base = (int32_t)((int64_t)c * kChunkCells) + src.col_base;
+  const uint32_t n_cell = (uint32_t)hs_min<int64_t>(kChunkCells, N - (int64_t)c * kChunkCells);
   if (tid < kChunkSlabs) hist[tid] = 0u;
   if (tid < kTM) {
     const int64_t pos = (int64_t)t * kTM + tid;
@@ -206,30 +226,31 @@ k_tile_fill(const TileSrc src, const int32_t* __restrict__ sorted_rows, int64_t 
   }
   __syncthreads();
   bool bad = false;
-  // pass 1: entries per slab (four batches of 32 entries loaded before the first is used: the loop is
-  // latency-bound otherwise)
-  constexpr int kU = 4;
+  auto load_rel = [&](const int64_t b, uint32_t i, uint32_t a1) -> uint32_t {
+    if (i >= a1) return 0xffffffffu;
+    const int32_t cid = PAIRS ? (int32_t)__ldg(&src.pairs[b + i].x) : __ldg(src.cols + b + i);
+    return (uint32_t)(cid - base);
+  };
+  // pass 1: entries per slab; two batches of 32 in flight per warp
   for (int r = warp; r < kTM; r += kFillThreads / 32) {
     const int64_t b = row_beg[r];
     const uint32_t a0 = row_a[r], a1 = row_b[r];
-    for (uint32_t i0 = a0; i0 < a1; i0 += 32 * kU) {
-      int64_t cell[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const uint32_t i = i0 + 32 * u + lane;
-        cell[u] = i < a1 ? (int64_t)src_col(src, b + i) : (int64_t)-1 - (int64_t)0x7fffffff;
+    for (uint32_t i0 = a0; i0 < a1; i0 += 64) {
+      const uint32_t rel0 = load_rel(b, i0 + lane, a1), rel1 = load_rel(b, i0 + 32 + lane, a1);
+      int head, len;
+      {
+        const bool ok = rel0 < n_cell;
+        bad |= (i0 + lane < a1) && !ok;                 // the search assumed ascending ids
+        const int s = ok ? (int)(rel0 >> 6) : -1;
+        lane_run(s, lane, head, len);
+        if (ok && lane == head) atomicAdd(&hist[s], (unsigned)len);
       }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        if (i0 + 32 * u >= a1) break;     // warp-uniform
-        const bool has = i0 + 32 * u + lane < a1;
-        int s = -1;
-        if (has) {
-          if (cell[u] < cell0 || cell[u] >= cell1) bad = true;      // the search assumed ascending ids
-          else s = (int)((cell[u] - cell0) >> 6);
-        }
-        const unsigned m = __match_any_sync(0xffffffffu, s);
-        if (s >= 0 && lane == __ffs(m) - 1) atomicAdd(&hist[s], (unsigned)__popc(m));
+      if (i0 + 32 < a1) {                               // warp-uniform
+        const bool ok = rel1 < n_cell;
+        bad |= (i0 + 32 + lane < a1) && !ok;
+        const int s = ok ? (int)(rel1 >> 6) : -1;
+        lane_run(s, lane, head, len);
+        if (ok && lane == head) atomicAdd(&hist[s], (unsigned)len);
       }
     }
   }
@@ -261,50 +282,52 @@ k_tile_fill(const TileSrc src, const int32_t* __restrict__ sorted_rows, int64_t 
   __syncthreads();
   // pass 2: place
   uint2* out = entries + rbase;
+  auto place = [&](uint32_t rel, float xv, uint32_t roff, uint32_t c8) {
+    const bool ok = rel < n_cell;
+    const int s = ok ? (int)(rel >> 6) : -1;
+    int head, len;
+    lane_run(s, lane, head, len);
+    unsigned int at = 0;
+    if (ok && lane == head) at = atomicAdd(&cursor[s], (unsigned)len);
+    at = __shfl_sync(0xffffffffu, at, head) + (unsigned)(lane - head);
+    if (ok) {
+      const uint32_t k = rel & 63u;
+      const uint32_t off = roff | ((k >> 3) << 11) | ((k & 7u) << 7) | (((c8 ^ k) & 7u) << 4);
+      const __half h = __float2half_rn(xv);
+      const __half l = __float2half_rn((xv - __half2float(h)) * kLoScale);
+      bad |= !(fabsf(xv) <= 65504.f);                   // fp16 overflow, Inf, NaN: the fp32 kernel scores the call
+      out[at] = make_uint2(off, (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16));
+    }
+  };
   for (int r = warp; r < kTM; r += kFillThreads / 32) {
     const int64_t b = row_beg[r];
     const uint32_t a0 = row_a[r], a1 = row_b[r];
-    for (uint32_t i0 = a0; i0 < a1; i0 += 32 * kU) {
-      int64_t cell[kU];
-      float x[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const uint32_t i = i0 + 32 * u + lane;
-        cell[u] = -1;
-        x[u] = 0.f;
-        if (i < a1) {
-          if (src.pairs) {
-            const uint2 e = __ldg(src.pairs + b + i);
-            cell[u] = (int64_t)(int)e.x - src.col_base;
-            x[u] = __uint_as_float(e.y);
-          } else {
-            cell[u] = (int64_t)__ldg(src.cols + b + i) - src.col_base;
-            x[u] = __ldg(src.vals + b + i);
-          }
+    const uint32_t roff = ((uint32_t)(r >> 6) << 10) | ((uint32_t)(r & 7) << 1), c8 = (uint32_t)(r >> 3) & 7u;
+    for (uint32_t i0 = a0; i0 < a1; i0 += 64) {
+      uint32_t rel0 = 0xffffffffu, rel1 = 0xffffffffu;
+      float x0 = 0.f, x1 = 0.f;
+      if (i0 + lane < a1) {
+        if (PAIRS) {
+          const uint2 e = __ldg(src.pairs + b + i0 + lane);
+          rel0 = (uint32_t)((int32_t)e.x - base);
+          x0 = __uint_as_float(e.y);
+        } else {
+          rel0 = (uint32_t)(__ldg(src.cols + b + i0 + lane) - base);
+          x0 = __ldg(src.vals + b + i0 + lane);
         }
       }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        if (i0 + 32 * u >= a1) break;     // warp-uniform
-        int s = -1, k = 0;
-        if (i0 + 32 * u + lane < a1 && cell[u] >= cell0 && cell[u] < cell1) {
-          s = (int)((cell[u] - cell0) >> 6);
-          k = (int)((cell[u] - cell0) & 63);
-        }
-        const unsigned m = __match_any_sync(0xffffffffu, s);
-        const int leader = __ffs(m) - 1;
-        unsigned int at = 0;
-        if (s >= 0 && lane == leader) at = atomicAdd(&cursor[s], (unsigned)__popc(m));
-        at = __shfl_sync(0xffffffffu, at, leader) + (unsigned)__popc(m & ((1u << lane) - 1u));
-        if (s >= 0) {
-          const float xv = x[u];
-          const __half h = __float2half_rn(xv);
-          const float hf = __half2float(h);
-          if (!(fabsf(xv) <= 65504.f)) bad = true;            // fp16 overflow, Inf, NaN: the fp32 kernel scores the call
-          const __half l = __float2half_rn((xv - hf) * kLoScale);
-          out[at] = make_uint2(elem_off(r, k), (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16));
+      if (i0 + 32 + lane < a1) {
+        if (PAIRS) {
+          const uint2 e = __ldg(src.pairs + b + i0 + 32 + lane);
+          rel1 = (uint32_t)((int32_t)e.x - base);
+          x1 = __uint_as_float(e.y);
+        } else {
+          rel1 = (uint32_t)(__ldg(src.cols + b + i0 + 32 + lane) - base);
+          x1 = __ldg(src.vals + b + i0 + 32 + lane);
         }
       }
+      place(rel0, x0, roff, c8);
+      if (i0 + 32 < a1) place(rel1, x1, roff, c8);      // warp-uniform
     }
   }
   if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(flags, 1);
@@ -393,7 +416,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
   const int n_st = hs_max(0, hs_min(p.n_slabs, s0 + p.slabs_per_seg) - s0);
   const int n_tiles = (2 * pair + 1 < p.n_tr) ? 2 : 1;
   // development aid: cycles each non-epilogue role of one mid-grid CTA spends blocked on each barrier
-  const bool dbg_on = p.dbg != nullptr && blockIdx.x == gridDim.x / 2 && warp < kEpiWarp0;
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == gridDim.x / 2 && warp >= kEpiWarps;
   long long w_acc[3] = {0, 0, 0};
   auto twait = [&](uint32_t bar, uint32_t parity, int slot) {
     if (dbg_on) {
@@ -423,13 +446,13 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kLoaderWarp) {
     // ================= entry chunks: runs ahead of the stages as far as the rings allow =================
     // A tile row's entries of consecutive slabs are one contiguous stream (regions are laid out chunk after chunk),
     // so the stream is prefetched into L2 by address, kEntryLookahead bytes ahead of the stage being fetched: the
@@ -487,7 +510,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
         } while (done < cnt);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.npad);
@@ -517,9 +540,9 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
         umma_commit(stage_empty(st));
       }
     }
-  } else if (warp < 4) {
-    // ================= A producers: warp 2 -> tile row 0, warp 3 -> tile row 1 =================
-    const int t = warp - 2;
+  } else if (warp >= kProducerWarp0) {
+    // ================= A producers: one warp per tile row =================
+    const int t = warp - kProducerWarp0;
     if (t < n_tiles) {
       uint32_t seq = 0;
       for (int i = 0; i < n_st; ++i) {
@@ -576,7 +599,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
     }
   } else {
     // ================= epilogue: TMEM -> fp32 registers -> fp64 =================
-    const int ew = warp - kEpiWarp0;
+    const int ew = warp;
     const int q = warp & 3, half = (ew >> 2) & 1, t = ew >> 3;
     if (t < n_tiles) {
       const int64_t pos = ((int64_t)(2 * pair + t)) * kTM + 32 * q + lane;     // sorted position of this thread's row
@@ -649,16 +672,16 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
   if (dbg_on && lane == 0) {
     // [0] total, [1] stages | loader: [2] ring_empty | mma: [3] acc_empty [4] a_full [5] b_full |
     // producer 0: [6] stage_empty [7] ring_full | producer 1: [8] stage_empty [9] ring_full
-    if (warp == 0) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = n_st; p.dbg[2] = w_acc[0]; }
-    if (warp == 1) { p.dbg[3] = w_acc[0]; p.dbg[4] = w_acc[1]; p.dbg[5] = w_acc[2]; }
-    if (warp == 2) { p.dbg[6] = w_acc[0]; p.dbg[7] = w_acc[1]; }
-    if (warp == 3) { p.dbg[8] = w_acc[0]; p.dbg[9] = w_acc[1]; }
+    if (warp == kLoaderWarp) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = n_st; p.dbg[2] = w_acc[0]; }
+    if (warp == kMmaWarp) { p.dbg[3] = w_acc[0]; p.dbg[4] = w_acc[1]; p.dbg[5] = w_acc[2]; }
+    if (warp == kProducerWarp0) { p.dbg[6] = w_acc[0]; p.dbg[7] = w_acc[1]; }
+    if (warp == kProducerWarp0 + 1) { p.dbg[8] = w_acc[0]; p.dbg[9] = w_acc[1]; }
   }
   // ---- teardown; the last CTA of this pair runs the KL epilogue ----
   tc_fence_before();
   __threadfence();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -752,6 +775,12 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   src.pairs = (const uint2*)pairs_dev;
   src.col_base = col_base;
 
+  const bool dbg = getenv("HS_TILE_DEBUG") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (dbg) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+  }
   // ---- step 1: bucketing ----
   k_tile_cuts<<<dim3(n_chunks + 1, n_tr), kTM, 0, st>>>(src, sorted_rows_dev, n_rows, N, n_chunks, cuts, flags);
   HS_LAUNCH_CHECK(ctx);
@@ -759,9 +788,15 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   HS_LAUNCH_CHECK(ctx);
   k_tile_scan<<<1, 1024, 0, st>>>(cap, n_regions, rbase);
   HS_LAUNCH_CHECK(ctx);
-  k_tile_fill<<<dim3(n_chunks, n_tr), kFillThreads, 0, st>>>(src, sorted_rows_dev, n_rows, N, n_chunks, n_slabs, cuts, rbase,
-                                                            (uint2*)ctx->tile_ent.p, tile_start, tile_cnt, flags);
+  if (dbg) cudaEventRecord(ev[1], st);
+  if (pairs_dev)
+    k_tile_fill<true><<<dim3(n_chunks, n_tr), kFillThreads, 0, st>>>(src, sorted_rows_dev, n_rows, N, n_chunks, n_slabs, cuts,
+                                                                    rbase, (uint2*)ctx->tile_ent.p, tile_start, tile_cnt, flags);
+  else
+    k_tile_fill<false><<<dim3(n_chunks, n_tr), kFillThreads, 0, st>>>(src, sorted_rows_dev, n_rows, N, n_chunks, n_slabs, cuts,
+                                                                     rbase, (uint2*)ctx->tile_ent.p, tile_start, tile_cnt, flags);
   HS_LAUNCH_CHECK(ctx);
+  if (dbg) cudaEventRecord(ev[2], st);
 
   // ---- step 2: MMA ----
   // cell segments: enough CTAs for ~8 waves (the tail is then one short CTA), at least 64 stages each;
@@ -801,7 +836,6 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   prm.out_n_perm = out_n_perm;
   prm.out_n_sel = out_n_sel;
   prm.flags = flags;
-  const bool dbg = getenv("HS_TILE_DEBUG") != nullptr;
   prm.dbg = nullptr;
   if (dbg) {
     HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
@@ -813,7 +847,14 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   HS_LAUNCH_CHECK(ctx);
   if (dbg) {
     long long h[16] = {0};
+    cudaEventRecord(ev[3], st);
     cudaStreamSynchronize(st);
+    float t_cut = 0, t_fill = 0, t_mma = 0;
+    cudaEventElapsedTime(&t_cut, ev[0], ev[1]);
+    cudaEventElapsedTime(&t_fill, ev[1], ev[2]);
+    cudaEventElapsedTime(&t_mma, ev[2], ev[3]);
+    for (auto& e : ev) cudaEventDestroy(e);
+    fprintf(stderr, "[tile dbg] cuts+scan %.3f ms, fill %.3f ms, mma %.3f ms\n", t_cut, t_fill, t_mma);
     cudaMemcpy(h, prm.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tile dbg] rows %lld pairs %d seg %d | CTA: %lld clk over %lld stages (%.0f/stage) | loader wait ring_empty %lld | "
                     "mma wait acc_empty %lld a_full %lld b_full %lld | producer0 wait stage_empty %lld ring_full %lld | "

@@ -240,6 +240,56 @@ class DeviceContext:
         if dist.get_rank(group) != src:
             self.density_commit(n_cells, n_grid)
 
+    def density_sharded_dev(self, x_dev, grid_dev, w_q_dev=None, group=None, rank=None, world=None, all_gather=None):
+        """The density stage with the cells sharded over the ranks of `group` (hs_density_shard_*): every rank
+        computes 1 / world of the distances and densities; three in-place all-gathers (row minima 8 B per cell,
+        density rows, per-block column sums) leave every rank with the state hs_density_dev would have produced,
+        bit for bit.  `all_gather(buffer_ptr, bytes_per_rank)` may replace the torch.distributed collective
+        (tests drive several ranks' parts through one context that way)."""
+        import torch
+        import torch.distributed as dist
+        d, n = x_dev.shape
+        d2, g = grid_dev.shape
+        if d != d2:
+            raise ValueError("Coordinates and grid points have different number of columns.")
+        if world is None:
+            world = dist.get_world_size(group) if dist.is_initialized() else 1
+            rank = dist.get_rank(group) if dist.is_initialized() else 0
+        dev = torch.device("cuda", self.device)
+
+        def gather(ptr, per):
+            if all_gather is not None:
+                return all_gather(ptr, per)
+            if world == 1:
+                return
+            self.synchronize()
+            whole = _wrap_device_ptr(ptr, per * world, dev)
+            dist.all_gather_into_tensor(whole, whole[rank * per:(rank + 1) * per], group=group)
+            torch.cuda.current_stream(dev).synchronize()
+
+        self._check(self._lib.hs_density_shard_dist_dev(self._h, _dptr(x_dev), n, d, _dptr(grid_dev), g, int(rank), int(world)),
+                    "hs_density_shard_dist_dev")
+        rm, dd, qp = C.c_void_p(None), C.c_void_p(None), C.c_void_p(None)
+        rmb, ddb, qpb = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.hs_density_shard_buffers(self._h, n, g, int(world), C.byref(rm), C.byref(rmb), C.byref(dd),
+                                                       C.byref(ddb), C.byref(qp), C.byref(qpb)), "hs_density_shard_buffers")
+        gather(rm.value, rmb.value)
+        self._check(self._lib.hs_density_shard_dens_dev(self._h, n, g, _dptr(w_q_dev), int(rank), int(world)),
+                    "hs_density_shard_dens_dev")
+        gather(dd.value, ddb.value)
+        gather(qp.value, qpb.value)
+        bw = C.c_double(0.0)
+        q = np.empty(g, dtype=np.float64)
+        self._check(self._lib.hs_density_shard_finish(self._h, n, g, C.byref(bw), _ptr(q)), "hs_density_shard_finish")
+        return dict(bandwidth=float(bw.value), Q=q)
+
+    def dkl_perm_csr_seeded_units_dev(self, gene_ptr_dev, val_dev, n_perm, seed, unit_stream_dev, out_dev):
+        """hs_dkl_perm_csr_seeded_units_dev: unit u / randomization r draws from stream unit_stream_dev[u] + r."""
+        n_units = gene_ptr_dev.numel() - 1
+        self._check(self._lib.hs_dkl_perm_csr_seeded_units_dev(self._h, _dptr(gene_ptr_dev), n_units, _dptr(val_dev),
+                                                               int(n_perm), int(seed) % (1 << 64), _dptr(unit_stream_dev),
+                                                               _dptr(out_dev)), "hs_dkl_perm_csr_seeded_units_dev")
+
     # -- K2/K3 --------------------------------------------------------------------------------
     def dkl_dense(self, expression) -> np.ndarray:
         """expression: (M, N) genes x cells; any layout, passed as an R matrix (column-major fp64)."""
