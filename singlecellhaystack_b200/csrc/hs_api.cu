@@ -127,6 +127,12 @@ struct HostPool {
 static int host_threads() {
   int n = (int)std::thread::hardware_concurrency();
   if (n <= 0) n = 1;
+  // one process per GPU: the ranks of a node share its cores (torchrun exports LOCAL_WORLD_SIZE); eight ranks
+  // with sixteen threads each on a 32-core host spent their time context switching
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+    const int lw = atoi(e);
+    if (lw > 1) n = std::max(1, n / lw);
+  }
   n = std::min(n, 16);
   if (const char* e = getenv("HS_HOST_THREADS")) {
     const int v = atoi(e);
@@ -148,6 +154,33 @@ static void narrow_f64(hs_ctx* ctx, const double* src, float* dst, int64_t n) {
     const int64_t a = std::min<int64_t>(n, (int64_t)t * per), b = std::min<int64_t>(n, a + per);
     for (int64_t i = a; i < b; ++i) dst[i] = (float)src[i];
   });
+}
+
+// dst[i] = src[i] over the pool: moves a block of pageable caller memory into a pinned ring buffer at host memory
+// bandwidth (a cudaMemcpyAsync from pageable memory is staged by the driver on one thread and blocks the caller)
+static void copy_bytes(hs_ctx* ctx, const void* src, void* dst, size_t n) {
+  if (n < ((size_t)1 << 20) || host_threads() == 1) {
+    memcpy(dst, src, n);
+    return;
+  }
+  if (!ctx->pool) ctx->pool = new HostPool(host_threads());
+  const int nt = ctx->pool->size();
+  const size_t per = ((n + nt - 1) / nt + 63) & ~(size_t)63;
+  ctx->pool->run([=](int t) {
+    const size_t a = std::min(n, (size_t)t * per), b = std::min(n, a + per);
+    if (b > a) memcpy((char*)dst + a, (const char*)src + a, b - a);
+  });
+}
+
+// true when a host pointer is ordinary pageable memory (not cudaHostAlloc / cudaHostRegister memory)
+static bool is_pageable(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return at.type == cudaMemoryTypeUnregistered;
 }
 
 static int ensure_ring(hs_ctx* ctx, size_t bytes) {
@@ -474,16 +507,28 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   HS_TRY(hs_ensure(ctx, ctx->cols32, sizeof(int32_t) * (size_t)hs_max<int64_t>(n_ids, 1)));
   HS_TRY(hs_ensure(ctx, ctx->vals32, sizeof(float) * (size_t)hs_max<int64_t>(n_vals, 1)));
   const size_t stage_vals = (size_t)hs_min<int64_t>((int64_t)chunk, hs_max<int64_t>(n_vals, 1));
+  int ring_k = 0;
   // fp64 values: narrowed on the host into a pinned ring (default), or uploaded as doubles and narrowed by
   // a kernel (HS_NARROW_ON_DEVICE=1); both give the same fp32 bits
-  const bool narrow_on_device = env_size("HS_NARROW_ON_DEVICE", 0) != 0;
-  if (!vals_f32) {
-    if (narrow_on_device)
-      HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * stage_vals));
-    else
-      HS_TRY(ensure_ring(ctx, sizeof(float) * stage_vals));
-  }
-  int ring_k = 0;
+  // (with fewer than four host threads to spare the host would be the bottleneck: the doubles cross the link and a
+  //  kernel narrows them)
+  const bool narrow_on_device = getenv("HS_NARROW_ON_DEVICE") ? env_size("HS_NARROW_ON_DEVICE", 0) != 0 : host_threads() < 4;
+  // R vectors (and numpy arrays) are pageable: their ids are bounced through the pinned ring by the host threads,
+  // like the values, instead of being handed to cudaMemcpyAsync directly (HS_NO_ID_BOUNCE=1: old behaviour)
+  const bool bounce_ids = !perm && !narrow_on_device && is_pageable(ids) && env_size("HS_NO_ID_BOUNCE", 0) == 0;
+  const bool bounce_f32 = vals_f32 && bounce_ids;
+  if (!vals_f32 && narrow_on_device) HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(double) * stage_vals));
+  if ((!vals_f32 && !narrow_on_device) || bounce_ids) HS_TRY(ensure_ring(ctx, sizeof(float) * stage_vals));
+  auto ring_take = [&](int& k_out) -> int {
+    const int k = ring_k;
+    ring_k = (ring_k + 1) % hs_ctx::kRing;
+    if (ctx->ring_busy[k]) {
+      HS_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[k]));
+      ctx->ring_busy[k] = false;
+    }
+    k_out = k;
+    return HS_OK;
+  };
   cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
 
   // row pointers rebased to the uploaded arrays
@@ -535,22 +580,35 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
       }
     for (int64_t off = a0; off < a1; off += (int64_t)stage_vals) {
       const int64_t n = hs_min<int64_t>((int64_t)stage_vals, a1 - off);
-      if (!perm)
+      if (!perm && bounce_ids) {
+        int k = 0;
+        HS_TRY(ring_take(k));
+        copy_bytes(ctx, ids + v0 + off, ctx->ring[k], sizeof(int32_t) * (size_t)n);
+        HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ctx->ring[k], sizeof(int32_t) * (size_t)n,
+                                     cudaMemcpyHostToDevice, cs));
+        HS_CUDA(ctx, cudaEventRecord(ctx->ev_ring[k], cs));
+        ctx->ring_busy[k] = true;
+      } else if (!perm) {
         HS_CUDA(ctx, cudaMemcpyAsync((int32_t*)ctx->cols32.p + off, ids + v0 + off, sizeof(int32_t) * (size_t)n,
                                      cudaMemcpyHostToDevice, cs));
-      if (vals_f32) {
+      }
+      if (bounce_f32) {
+        int k = 0;
+        HS_TRY(ring_take(k));
+        copy_bytes(ctx, vals32h + v0 + off, ctx->ring[k], sizeof(float) * (size_t)n);
+        HS_CUDA(ctx, cudaMemcpyAsync((float*)ctx->vals32.p + off, ctx->ring[k], sizeof(float) * (size_t)n,
+                                     cudaMemcpyHostToDevice, cs));
+        HS_CUDA(ctx, cudaEventRecord(ctx->ev_ring[k], cs));
+        ctx->ring_busy[k] = true;
+      } else if (vals_f32) {
         HS_CUDA(ctx, cudaMemcpyAsync((float*)ctx->vals32.p + off, vals32h + v0 + off, sizeof(float) * (size_t)n,
                                      cudaMemcpyHostToDevice, cs));
       } else if (narrow_on_device) {
         HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[0].p, vals + v0 + off, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, cs));
         HS_TRY(hs_run_f64_to_f32(ctx, (const double*)ctx->stage_x[0].p, (float*)ctx->vals32.p + off, n, cs));
       } else {
-        const int k = ring_k;
-        ring_k = (ring_k + 1) % hs_ctx::kRing;
-        if (ctx->ring_busy[k]) {
-          HS_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[k]));
-          ctx->ring_busy[k] = false;
-        }
+        int k = 0;
+        HS_TRY(ring_take(k));
         narrow_f64(ctx, vals + v0 + off, (float*)ctx->ring[k], n);
         HS_CUDA(ctx, cudaMemcpyAsync((float*)ctx->vals32.p + off, ctx->ring[k], sizeof(float) * (size_t)n,
                                      cudaMemcpyHostToDevice, cs));

@@ -353,6 +353,7 @@ struct TileMmaParams {
   int64_t out_n_sel;
   const int* flags;                       // bit 0 set by the bucketing: the fallback kernel owns the output
   long long* dbg;                         // optional (HS_TILE_DEBUG): cycles the roles of one CTA spend waiting
+  int dbg_block;                          // the CTA that reports (HS_TILE_DEBUG=<tile row>; default: mid-grid)
 };
 
 __device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {     // bytes: multiple of 16
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
   const int n_st = hs_max(0, hs_min(p.n_slabs, s0 + p.slabs_per_seg) - s0);
   const int n_tiles = (2 * pair + 1 < p.n_tr) ? 2 : 1;
   // development aid: cycles each non-epilogue role of one mid-grid CTA spends blocked on each barrier
-  const bool dbg_on = p.dbg != nullptr && blockIdx.x == gridDim.x / 2 && warp >= kEpiWarps;
+  const bool dbg_on = p.dbg != nullptr && (int)blockIdx.x == p.dbg_block && warp >= kEpiWarps;
   long long w_acc[3] = {0, 0, 0};
   auto twait = [&](uint32_t bar, uint32_t parity, int slot) {
     if (dbg_on) {
@@ -717,6 +718,328 @@ __global__ void __launch_bounds__(kMmaThreads, 1) k_tile_mma(const TileMmaParams
   }
 }
 
+// ---- step 2, second form: one tile row per CTA, three operand stages, three acc0 buffers -----------------------------
+// Measured on the two-tile kernel above (HS_TILE_DEBUG): a tcgen05.commit reaches the waiting warps ~1000 clk after it
+// is issued, so the round trip "MMAs of a stage done -> epilogue woken -> TMEM drained -> issuer released" is ~1800 clk
+// while a tile row's stage is ~700-1200 clk of MMA work: with one acc0 buffer per tile row the tensor pipe idles, and
+// with two operand stages the producers start late.  This form hides both hops: acc0 is triple-buffered
+// (3 x 128 + 128 columns of acc1 = all of TMEM), the operand ring is three stages deep (3 x 64 KB), and the CTA owns a
+// single tile row (the B operand is no longer shared between two tile rows; it comes out of L2).
+constexpr int kS1 = 3;                                   // operand stages = acc0 buffers
+// 32 KB of entries in flight; few large chunks: the loader spends ~500 clk per chunk whatever its size (measured:
+// 13 chunks of 512 entries per stage made the densest tile rows loader-bound at 7300 clk per stage)
+constexpr int kRing1Slots = 4, kRing1Entries = 1024, kRing1SlotBytes = kRing1Entries * 8;
+constexpr int kProducers1 = 4;                           // A-producer warps (the scatter runs at ~0.5 entries/clk per warp)
+constexpr int kMma1Threads = 32 * (10 + kProducers1);    // warps 0-7 epilogue, 8 loader, 9.. producers, last: MMA issuer
+constexpr size_t kSmem1Stage = (size_t)kATileBytes + kBStageBytes;          // 64 KB: A_hi, A_lo, D_hi, D_lo
+constexpr size_t kSmem1 = 1024 + kS1 * kSmem1Stage + kRing1Slots * kRing1SlotBytes + 512;
+
+__global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaParams p) {
+  if (*p.flags & 1) return;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t st_base = smem_u32(smem);
+  const uint32_t ring_base = st_base + (uint32_t)(kS1 * kSmem1Stage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kS1 * kSmem1Stage + kRing1Slots * kRing1SlotBytes);
+  const uint32_t bar_base = smem_u32(bars);
+  uint32_t* ring_meta = reinterpret_cast<uint32_t*>(bars + 32);
+  uint32_t* tmem_slot = ring_meta + kRing1Slots;
+  uint32_t* last_flag = tmem_slot + 1;
+  auto a_full = [&](int st) { return bar_base + 8u * st; };                      // 0..2   (the producer warps)
+  auto b_full = [&](int st) { return bar_base + 8u * (3 + st); };                // 3..5   (tx)
+  auto stage_empty = [&](int st) { return bar_base + 8u * (6 + st); };           // 6..8   (commit)
+  auto acc_full = [&](int b) { return bar_base + 8u * (9 + b); };                // 9..11  (commit)
+  auto acc_empty = [&](int b) { return bar_base + 8u * (12 + b); };              // 12..14 (8 epilogue warps)
+  auto ring_full = [&](int sl) { return bar_base + 8u * (15 + sl); };                    // 15..22 (tx)
+  auto ring_empty = [&](int sl) { return bar_base + 8u * (15 + kRing1Slots + sl); };     // 23..30 (the producer warps)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tr = blockIdx.x % p.n_tr, seg = blockIdx.x / p.n_tr;
+  const int s0 = seg * p.slabs_per_seg;
+  const int n_st = hs_max(0, hs_min(p.n_slabs, s0 + p.slabs_per_seg) - s0);
+  constexpr int kLoader = 8, kProd0 = 9, kIssuer = 9 + kProducers1;
+  // development aid (HS_TILE_DEBUG): cycles the non-epilogue roles of one mid-grid CTA spend blocked on each barrier
+  const bool dbg_on = p.dbg != nullptr && (int)blockIdx.x == p.dbg_block && warp >= 8;
+  long long w_acc[3] = {0, 0, 0};
+  auto twait = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (dbg_on) {
+      const long long t0 = clock64();
+      mbar_wait(bar, parity);
+      w_acc[slot] += clock64() - t0;
+    } else {
+      mbar_wait(bar, parity);
+    }
+  };
+  const long long t_begin = clock64();
+
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kS1; ++st) {
+      mbar_init(a_full(st), kProducers1);
+      mbar_init(b_full(st), 1);
+      mbar_init(stage_empty(st), 1);
+      mbar_init(acc_full(st), 1);
+      mbar_init(acc_empty(st), 8);
+    }
+    for (int sl = 0; sl < kRing1Slots; ++sl) {
+      mbar_init(ring_full(sl), 1);
+      mbar_init(ring_empty(sl), kProducers1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kIssuer) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto a_addr = [&](int st) { return st_base + (uint32_t)(st * kSmem1Stage); };
+  auto b_addr = [&](int st) { return st_base + (uint32_t)(st * kSmem1Stage) + (uint32_t)kATileBytes; };
+
+  if (warp == kLoader) {
+    // ================= entry chunks through a ring, running ahead; the stream is prefetched into L2 =================
+    unsigned long long m_start = 0ull;     // lane l: metadata of stage (base + l)
+    uint32_t m_cnt = 0u;
+    uint32_t seq = 0u;
+    unsigned long long pf_pos = 0ull, pf_end = 0ull;
+    if (n_st > 0) {
+      const size_t i0 = (size_t)tr * p.n_slabs + s0, i1 = i0 + (size_t)(n_st - 1);
+      pf_pos = p.tile_start[i0];
+      pf_end = p.tile_start[i1] + p.tile_cnt[i1];
+    }
+    for (int i = 0; i < n_st; ++i) {
+      if ((i & 31) == 0) {
+        m_start = 0ull;
+        m_cnt = 0u;
+        if (i + lane < n_st) {
+          const size_t idx = (size_t)tr * p.n_slabs + (s0 + i + lane);
+          m_start = p.tile_start[idx];
+          m_cnt = p.tile_cnt[idx];
+        }
+      }
+      const unsigned long long start = __shfl_sync(0xffffffffu, m_start, i & 31);
+      const uint32_t cnt = __shfl_sync(0xffffffffu, m_cnt, i & 31);
+      if (lane == 0) {
+        const unsigned long long want = hs_min<unsigned long long>(pf_end, start + kEntryLookahead / 8);
+        unsigned long long pos = hs_max<unsigned long long>(pf_pos, start) & ~511ull;     // 4 KB steps
+        for (; pos < want; pos += 512) l2_prefetch(p.entries + pos, 4096);
+        pf_pos = pos;
+      }
+      uint32_t done = 0;
+      do {
+        const uint32_t n = hs_min<uint32_t>(kRing1Entries, cnt - done);
+        const int sl = (int)(seq % kRing1Slots);
+        if (seq >= kRing1Slots) twait(ring_empty(sl), ((seq / kRing1Slots) - 1) & 1, 0);
+        if (lane == 0) {
+          const bool last = done + n >= cnt;
+          ring_meta[sl] = n | (last ? 0x80000000u : 0u);
+          const uint32_t bytes = ((n + 1) & ~1u) * 8u;
+          if (bytes) {
+            mbar_arrive_expect_tx(ring_full(sl), bytes);
+            bulk_g2s(ring_base + (uint32_t)sl * kRing1SlotBytes, p.entries + start + done, bytes, ring_full(sl));
+          } else {
+            mbar_arrive(ring_full(sl));
+          }
+        }
+        __syncwarp();
+        ++seq;
+        done += n;
+      } while (done < cnt);
+    }
+  } else if (warp == kIssuer) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.npad);
+      const uint32_t acc1 = tmem_base + 384u;
+      for (int i = 0; i < n_st; ++i) {
+        const int st = i % kS1;
+        const uint32_t use = (uint32_t)(i / kS1);
+        const bool window_start = (i % kFlushStages) == 0;
+        // acc1 restarts: the drain of the previous window's last stage (it reads acc1) must be over
+        if (window_start && i > 0) twait(acc_empty((i - 1) % kS1), ((i - 1) / kS1) & 1, 0);
+        if (i >= kS1) twait(acc_empty(st), (use - 1) & 1, 0);
+        twait(a_full(st), use & 1, 1);
+        twait(b_full(st), use & 1, 2);
+        tc_fence_after();
+        const uint32_t a_st = a_addr(st), b_st = b_addr(st);
+        const uint32_t acc0 = tmem_base + (uint32_t)(st * 128);
+#pragma unroll
+        for (int k16 = 0; k16 < kSlab / 16; ++k16) {
+          const uint32_t koff = (uint32_t)k16 * 2u * kSbo;
+          const uint64_t a_hi = make_desc(a_st + koff), a_lo = make_desc(a_st + kTileBytes + koff);
+          const uint64_t b_hi = make_desc(b_st + koff), b_lo = make_desc(b_st + kTileBytes + koff);
+          umma_f16(acc0, a_hi, b_hi, idesc, k16 == 0 ? 0u : 1u);
+          umma_f16(acc1, a_hi, b_lo, idesc, (window_start && k16 == 0) ? 0u : 1u);
+          umma_f16(acc1, a_lo, b_hi, idesc, 1u);
+        }
+        umma_commit(acc_full(st));
+        umma_commit(stage_empty(st));
+      }
+    }
+  } else if (warp >= kProd0) {
+    // ================= A producers: each zero-fills its share of the tile, then they take the entry chunks in turn ======
+    const int pw = warp - kProd0;
+    uint32_t seq = 0;
+    for (int i = 0; i < n_st; ++i) {
+      const int st = i % kS1;
+      const uint32_t use = (uint32_t)(i / kS1);
+      if (i >= kS1) twait(stage_empty(st), (use - 1) & 1, 0);
+      if (pw == 0 && lane == 0) {
+        const size_t pf = (size_t)(s0 + i + kBLookahead) * kTileBytes;
+        if (i + kBLookahead < n_st) {
+          l2_prefetch(p.Dh + pf, kTileBytes);
+          l2_prefetch(p.Dl + pf, kTileBytes);
+        }
+        const size_t off = (size_t)(s0 + i) * kTileBytes;
+        mbar_arrive_expect_tx(b_full(st), kBStageBytes);
+        bulk_g2s(b_addr(st), p.Dh + off, kTileBytes, b_full(st));
+        bulk_g2s(b_addr(st) + kTileBytes, p.Dl + off, kTileBytes, b_full(st));
+      }
+      const uint32_t a_hi = a_addr(st), a_lo = a_hi + kTileBytes;
+#pragma unroll 8
+      for (int z = 0; z < kATileBytes / kProducers1 / 512; ++z)
+        sts_zero16(a_hi + (uint32_t)pw * (kATileBytes / kProducers1) + (uint32_t)(z * 512 + lane * 16));
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kProducers1) : "memory");     // all of it zeroed before any warp scatters
+      for (;;) {
+        const int sl = (int)(seq % kRing1Slots);
+        twait(ring_full(sl), (seq / kRing1Slots) & 1, 1);
+        const uint32_t meta = ring_meta[sl];
+        if ((seq % kProducers1) == (uint32_t)pw) {
+          const uint32_t n = meta & 0x7fffffffu;
+          const uint32_t rb = ring_base + (uint32_t)sl * kRing1SlotBytes;
+          uint32_t e = lane;
+          for (; e + 96 < n; e += 128) {     // four entries in flight per lane
+            const uint2 e0 = lds_u2(rb + e * 8u), e1 = lds_u2(rb + (e + 32) * 8u);
+            const uint2 e2 = lds_u2(rb + (e + 64) * 8u), e3 = lds_u2(rb + (e + 96) * 8u);
+            sts_u16(a_hi + e0.x, e0.y); sts_u16(a_lo + e0.x, e0.y >> 16);
+            sts_u16(a_hi + e1.x, e1.y); sts_u16(a_lo + e1.x, e1.y >> 16);
+            sts_u16(a_hi + e2.x, e2.y); sts_u16(a_lo + e2.x, e2.y >> 16);
+            sts_u16(a_hi + e3.x, e3.y); sts_u16(a_lo + e3.x, e3.y >> 16);
+          }
+          for (; e < n; e += 32) {
+            const uint2 e0 = lds_u2(rb + e * 8u);
+            sts_u16(a_hi + e0.x, e0.y);
+            sts_u16(a_lo + e0.x, e0.y >> 16);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ring_empty(sl));
+        ++seq;
+        if (meta >> 31) break;
+      }
+      fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(st));
+    }
+  } else if (warp < 8) {
+    // ================= epilogue: TMEM -> fp32 registers -> fp64 =================
+    const int q = warp & 3, half = warp >> 2;
+    const int64_t pos = (int64_t)tr * kTM + 32 * q + lane;     // sorted position of this thread's row
+    const bool live = pos < p.n_rows;
+    const int col0 = 64 * half;
+    const int n8 = hs_max(0, hs_min(8, (p.npad - col0) >> 3));
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(32 * q) << 16);
+    double* prow = p.P64 + (int64_t)seg * p.seg_stride + pos * p.ldP;
+    const double unscale = 1.0 / (double)kScaleD;
+    for (int w0 = 0; w0 < n_st; w0 += kFlushStages) {
+      const int wend = hs_min(n_st, w0 + kFlushStages);
+      float acc2[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc2[c] = 0.f;
+      for (int i = w0; i < wend; ++i) {
+        const int st = i % kS1;
+        mbar_wait(acc_full(st), (i / kS1) & 1);
+        tc_fence_after();
+        const uint32_t acc0 = lane_addr + (uint32_t)(st * 128 + col0);
+#pragma unroll
+        for (int h = 0; h < 8; h += 2) {     // n8 is even; two loads in flight per wait
+          if (h < n8) {
+            uint32_t m0[8], m1[8];
+            tmem_ld8_nowait(acc0 + (uint32_t)(8 * h), m0);
+            tmem_ld8_nowait(acc0 + (uint32_t)(8 * h + 8), m1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc_add(acc2[8 * h + c], m0[c]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc_add(acc2[8 * h + 8 + c], m1[c]);
+          }
+        }
+        if (i == wend - 1) {     // the cross terms of the whole window, scale 2^-11
+#pragma unroll
+          for (int h = 0; h < 8; h += 2) {
+            if (h < n8) {
+              uint32_t a0[8], a1[8];
+              tmem_ld8_nowait(lane_addr + (uint32_t)(384 + col0 + 8 * h), a0);
+              tmem_ld8_nowait(lane_addr + (uint32_t)(384 + col0 + 8 * h + 8), a1);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc_fma(acc2[8 * h + c], a0[c], 1.0f / kLoScale);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc_fma(acc2[8 * h + 8 + c], a1[c], 1.0f / kLoScale);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(st));
+      }
+      if (live) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          if (col0 + c < p.G) {
+            // single writer per (segment, row, column): the order of the additions is fixed
+            if (w0 == 0) flush_store(prow + col0 + c, acc2[c], unscale);
+            else flush_add(prow + col0 + c, acc2[c], unscale);
+          }
+        }
+      }
+    }
+  }
+
+  if (dbg_on && lane == 0) {
+    if (warp == kLoader) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = n_st; p.dbg[2] = w_acc[0]; }
+    if (warp == kIssuer) { p.dbg[3] = w_acc[0]; p.dbg[4] = w_acc[1]; p.dbg[5] = w_acc[2]; }
+    if (warp == kProd0) { p.dbg[6] = w_acc[0]; p.dbg[7] = w_acc[1]; }
+    if (warp == kProd0 + 1) { p.dbg[8] = w_acc[0]; p.dbg[9] = w_acc[1]; }
+  }
+  // ---- teardown; the last CTA of this tile row runs the KL epilogue ----
+  tc_fence_before();
+  __threadfence();
+  __syncthreads();
+  if (warp == kIssuer) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(p.pair_done + tr, 1u);
+    *last_flag = (old == (unsigned int)(p.n_seg - 1)) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (*last_flag == 0u) return;
+  __threadfence();
+  for (int rr = warp; rr < kTM; rr += kMma1Threads / 32) {
+    const int64_t pos = (int64_t)tr * kTM + rr;
+    if (pos >= p.n_rows) break;
+    double pr[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int j = lane + 32 * a;
+      double sum = 0.0;
+      if (j < p.G)
+        for (int sg = 0; sg < p.n_seg; ++sg) sum += __ldcg(p.P64 + (int64_t)sg * p.seg_stride + pos * p.ldP + j);
+      pr[a] = sum;
+    }
+    const double kl = hs_kl_epilogue<4>(pr, p.Q, p.G, lane);
+    if (lane == 0) {
+      const int64_t row = p.sorted_rows[pos];
+      int64_t o = row;
+      if (p.out_n_perm > 0) {
+        const int64_t s = row / p.out_n_perm, r = row - s * p.out_n_perm;
+        o = s + r * p.out_n_sel;
+      }
+      p.out[o] = kl;
+    }
+  }
+}
+
 }  // namespace
 
 bool hs_tile_path_enabled(const hs_ctx* ctx) {
@@ -756,7 +1079,7 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   const size_t cap_b = up((size_t)(n_regions + 1) * 8);
   const size_t ts_b = up((size_t)n_tr * n_slabs * 8);
   const size_t tc_b = up((size_t)n_tr * n_slabs * 4);
-  const size_t pd_b = up((size_t)n_pairs * 4);
+  const size_t pd_b = up((size_t)n_tr * 4);      // completion counters: one per tile row (or pair)
   HS_TRY(hs_ensure(ctx, ctx->tile_ws, cuts_b + 2 * cap_b + ts_b + tc_b + pd_b));
   char* w = (char*)ctx->tile_ws.p;
   uint32_t* cuts = (uint32_t*)w;                               w += cuts_b;
@@ -801,7 +1124,10 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   // ---- step 2: MMA ----
   // cell segments: enough CTAs for ~8 waves (the tail is then one short CTA), at least 64 stages each;
   // blockIdx runs over the pairs first, so the CTAs in flight share a segment's density tiles through L2
-  int64_t want_seg = ((int64_t)ctx->sm_count * 8 + n_pairs - 1) / n_pairs;
+  int form = 1;      // 1: one tile row per CTA, three stages (k_tile_mma1); 2: two tile rows per CTA (k_tile_mma)
+  if (const char* e = getenv("HS_TILE_FORM")) form = atoi(e) == 2 ? 2 : 1;
+  const int n_units = form == 1 ? n_tr : n_pairs;
+  int64_t want_seg = ((int64_t)ctx->sm_count * 8 + n_units - 1) / n_units;
   if (const char* e = getenv("HS_TILE_SEGMENTS")) want_seg = hs_max(1, atoi(e));
   int n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(want_seg, n_slabs / 64));
   int slabs_per_seg = (n_slabs + n_seg - 1) / n_seg;
@@ -810,7 +1136,7 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   const int ldP = npad;
   const int64_t seg_stride = (int64_t)n_pairs * 2 * kTM * ldP;
   HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_seg * (size_t)seg_stride));
-  HS_CUDA(ctx, cudaMemsetAsync(pair_done, 0, (size_t)n_pairs * 4, st));
+  HS_CUDA(ctx, cudaMemsetAsync(pair_done, 0, (size_t)n_tr * 4, st));
 
   TileMmaParams prm;
   prm.entries = (const uint2*)ctx->tile_ent.p;
@@ -842,8 +1168,18 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
     HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
     prm.dbg = (long long*)((char*)ctx->umma_flags.p + 64);
   }
-  HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMma));
-  k_tile_mma<<<(unsigned)(n_pairs * n_seg), kMmaThreads, kSmemMma, st>>>(prm);
+  {
+    const int units = form == 1 ? n_tr : n_pairs;
+    int tr_dbg = dbg ? atoi(getenv("HS_TILE_DEBUG")) : 0;
+    prm.dbg_block = (n_seg / 2) * units + hs_min(hs_max(tr_dbg, 0), units - 1);      // a middle segment of that tile row
+  }
+  if (form == 1) {
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1));
+    k_tile_mma1<<<(unsigned)(n_tr * n_seg), kMma1Threads, kSmem1, st>>>(prm);
+  } else {
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMma));
+    k_tile_mma<<<(unsigned)(n_pairs * n_seg), kMmaThreads, kSmemMma, st>>>(prm);
+  }
   HS_LAUNCH_CHECK(ctx);
   if (dbg) {
     long long h[16] = {0};

@@ -24,7 +24,7 @@ from . import haystack as _hs
 from . import sparse as _sparse
 from . import splinefit as _fit
 
-__all__ = ["plan_gene_shards", "owner_of", "haystack_continuous_highD_sharded"]
+__all__ = ["plan_gene_shards", "owner_of", "deal_permutation_units", "DeviceShard", "haystack_continuous_highD_sharded"]
 
 
 def plan_gene_shards(work: np.ndarray, world: int) -> np.ndarray:
@@ -45,6 +45,85 @@ def plan_gene_shards(work: np.ndarray, world: int) -> np.ndarray:
 def owner_of(genes: np.ndarray, bounds: np.ndarray) -> np.ndarray:
     """Rank owning each gene index under `bounds`."""
     return (np.searchsorted(bounds, np.asarray(genes), side="right") - 1).astype(np.int64)
+
+
+def deal_permutation_units(costs, n_perm: int, world: int, block: int = 25):
+    """Split the randomization batch (R/haystack_continuous.R:245-284: S selected genes x R permutations) into
+    (gene position s, permutations [r_lo, r_hi)) units of `block` permutations and deal them to `world` ranks by
+    descending cost (longest processing time first), so that the fixed total of S x R permuted rows is balanced
+    however the selected genes are spread over the gene slices.  `costs[s]` = stored entries of selected gene s.
+    Returns one list of (s, r_lo, r_hi) per rank; deterministic, identical on every rank."""
+    costs = np.asarray(costs, dtype=np.float64)
+    block = max(1, min(int(block), int(n_perm)))
+    units = []
+    for s, c in enumerate(costs):
+        for r_lo in range(0, int(n_perm), block):
+            r_hi = min(int(n_perm), r_lo + block)
+            units.append((float(c) * (r_hi - r_lo), s, r_lo, r_hi))
+    units.sort(key=lambda u: (-u[0], u[1], u[2]))
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for cost, s, r_lo, r_hi in units:
+        r = min(range(world), key=lambda k: (load[k], k))
+        load[r] += cost
+        out[r].append((s, r_lo, r_hi))
+    return out
+
+
+class DeviceShard:
+    """One rank's part of the device-resident path, SPMD over the ranks of `group` (one process per GPU).
+
+    The three spans of the path and their exchange steps:
+      density()    K1.  "cells" (default with several ranks): every rank computes 1 / world of the cells and three
+                   in-place all-gathers rebuild the full state on every rank, bit-identical to one GPU
+                   (DeviceContext.density_sharded_dev); "broadcast": rank 0 computes, NCCL broadcasts;
+                   "replicate": every rank computes everything.
+      score()      K3 on this rank's gene slice (plan_gene_shards: contiguous, nnz-balanced).
+      randomize()  K4 on this rank's (gene, permutation block) units (deal_permutation_units), ONE batched call;
+                   unit u draws from the streams s * R + r of the whole job, so the randomized matrix does not
+                   depend on the number of ranks.
+      gather()     D_KL slices -> every rank (all-gather, padded to the longest slice).
+    """
+
+    def __init__(self, ctx, group=None, density_mode: str = "cells"):
+        import torch.distributed as dist
+        self.ctx = ctx
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if density_mode not in ("cells", "broadcast", "replicate"):
+            raise ValueError("density_mode must be 'cells', 'broadcast' or 'replicate'")
+        self.density_mode = density_mode
+
+    def density(self, x_dev, grid_dev, w_q_dev=None):
+        if self.world == 1 or self.density_mode == "replicate":
+            return self.ctx.density_dev(x_dev, grid_dev, w_q_dev)
+        if self.density_mode == "cells":
+            return self.ctx.density_sharded_dev(x_dev, grid_dev, w_q_dev, group=self.group)
+        out = self.ctx.density_dev(x_dev, grid_dev, w_q_dev) if self.rank == 0 else None
+        self.ctx.density_broadcast(x_dev.shape[1], grid_dev.shape[1], src=0, group=self.group)
+        return out
+
+    def score(self, p_dev, j_dev, x_dev, out_dev):
+        self.ctx.dkl_csr_dev(p_dev, j_dev, x_dev, out_dev)
+
+    def randomize(self, gene_ptr_dev, val_dev, n_perm_unit: int, seed: int, unit_stream_dev, out_dev):
+        if gene_ptr_dev.numel() > 1:
+            self.ctx.dkl_perm_csr_seeded_units_dev(gene_ptr_dev, val_dev, n_perm_unit, seed, unit_stream_dev, out_dev)
+
+    def gather(self, local_dev, bounds):
+        """All-gather the ranks' D_KL slices (genes [bounds[r], bounds[r+1]) on rank r) into one device vector."""
+        import torch
+        import torch.distributed as dist
+        if self.world == 1:
+            return local_dev
+        sizes = [int(bounds[r + 1] - bounds[r]) for r in range(self.world)]
+        pad = max(sizes)
+        send = torch.zeros(pad, dtype=local_dev.dtype, device=local_dev.device)
+        send[:sizes[self.rank]] = local_dev[:sizes[self.rank]]
+        recv = torch.empty(pad * self.world, dtype=local_dev.dtype, device=local_dev.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        return torch.cat([recv[r * pad:r * pad + sizes[r]] for r in range(self.world)])
 
 
 def _all_gather_rows(local: np.ndarray, group):

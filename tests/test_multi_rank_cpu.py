@@ -169,3 +169,20 @@ def test_device_draws_do_not_depend_on_world_size(toy):
     np.testing.assert_array_equal(out[0][0], out[1][0])
     np.testing.assert_array_equal(out[0][0], single["info"]["randomization"]["KLD_rand"])
     np.testing.assert_allclose(out[0][1], single["results"]["log.p.vals"].values, rtol=0, atol=1e-12)
+
+
+def test_deal_permutation_units_is_balanced_and_complete():
+    from singlecellhaystack_b200.distributed import deal_permutation_units
+    rng = np.random.default_rng(1)
+    costs = rng.integers(50, 200000, size=100)
+    for world in (1, 2, 4, 8):
+        deal = deal_permutation_units(costs, 100, world, block=25)
+        assert len(deal) == world
+        seen = sorted(u for part in deal for u in part)
+        assert seen == sorted((s, lo, lo + 25) for s in range(100) for lo in range(0, 100, 25))     # every unit once
+        load = [sum(costs[s] * (hi - lo) for s, lo, hi in part) for part in deal]
+        assert max(load) <= 1.02 * (sum(load) / world) + 25 * costs.max()                            # LPT bound
+        assert deal == deal_permutation_units(costs, 100, world, block=25)                          # deterministic
+    # ragged: R not a multiple of the block, fewer units than ranks
+    deal = deal_permutation_units([10, 20], 7, 4, block=3)
+    assert sorted(u for part in deal for u in part) == [(0, 0, 3), (0, 3, 6), (0, 6, 7), (1, 0, 3), (1, 3, 6), (1, 6, 7)]
