@@ -205,6 +205,15 @@ int hs_density_dev(hs_ctx* ctx, const double* x_dev, int64_t n_cells, int n_dims
                    const double* grid_dev, int n_grid, const double* w_q_dev,
                    double* bandwidth_out, double* q_out);
 
+/* ---- gene x grid profiles (the step after the path; optional) ------------------------------- */
+/* prepare_clustering (R/haystack_continuous.R:604-666), the input of hclust_haystack / kmeans_haystack
+ * (R/s3.R:213-253): per gene the column sums colSums(density * expression[g, ]) (:647 / :655), every row rescaled
+ * to sum to 1 (:664).  Same contraction as hs_dkl_csr / hs_dkl_dense without the KL reduction; uses the resident
+ * density state.  profile_out: n_genes x n_grid column-major doubles (an R matrix). */
+int hs_profile_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x,
+                   int64_t n_genes, double* profile_out);
+int hs_profile_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* profile_out);
+
 /* ---- row statistics (the step before the path; optional) ----------------------------------- */
 /* Matrix::rowMeans and the per-row sample sd (n-1 denominator, implicit zeros counted) of a CSR matrix --
  * R/haystack_continuous.R:57-74, the inputs of coeffVar (:222) and of the gene selection (:227-236).  Two

@@ -428,6 +428,28 @@ def get_log_p_D_KL_continuous(dkl_observed_, dkl_randomized, all_coeff_var, trai
 
 
 # --------------------------------------------------------------------------------------------
+# the step after the path: prepare_clustering (R/haystack_continuous.R:604-666)
+# --------------------------------------------------------------------------------------------
+def prepare_clustering(x, expression, grid_coordinates, scale=True) -> np.ndarray:
+    """Gene x grid densities, rows rescaled to sum to 1.  grid_coordinates are in the unscaled space (:612)."""
+    x = np.asarray(x, dtype=np.float64)
+    grid = np.asarray(grid_coordinates, dtype=np.float64)
+    if scale:
+        x, center, sc = scale_coords(x)                                          # :606-611
+        grid = (grid - center) / sc                                              # :612
+    dens = density_stage(x, grid)["density"]                                     # :624-632
+    m_ = expression.shape[0]
+    out = np.empty((m_, grid.shape[0]))
+    for g in range(m_):
+        if isinstance(expression, RowSparse):
+            w = extract_row_dgRMatrix(expression, g + 1)                          # :655
+        else:
+            w = np.asarray(expression[g], dtype=np.float64)                       # :647
+        out[g] = (dens * w[:, None]).sum(axis=0)
+    return out / out.sum(axis=1, keepdims=True)                                   # :664
+
+
+# --------------------------------------------------------------------------------------------
 # the whole path (R/haystack_continuous.R:27-339) with the random inputs supplied
 # --------------------------------------------------------------------------------------------
 def haystack_continuous_highD(x, expression, grid_coord, perm_source, sets_mean, sets_sd,

@@ -1,6 +1,7 @@
 # Drop-in replacement of the three hot spans of haystack_continuous_highD()
 # (singleCellHaystack R/haystack_continuous.R:168-186, :199-213, :245-284) by device calls.
-# WRITTEN BLIND (no R in the build environment); see INTEGRATION.md.
+# Written without an R interpreter (none in the build image): see INTEGRATION.md and tests/test_rshim_cpu.py for what
+# is checked statically and against a mock of the R C API.
 #
 # Usage inside the patched haystack_continuous_highD(), everything else of the function unchanged:
 #

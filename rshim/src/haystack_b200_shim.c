@@ -1,8 +1,9 @@
 /* .Call shim between R and libhaystack_b200.so (C ABI: include/haystack_b200.h).
  *
- * WRITTEN BLIND: neither the build container nor the GPU boxes have R (no Rinternals.h), so this
- * file has never been compiled.  It is the binding a maintainer adds to singleCellHaystack to put
- * the B200 path behind the unchanged haystack() API.  Rules it follows:
+ * Neither the build container nor the GPU boxes have R (no Rinternals.h), so this file is compiled and RUN against a
+ * miniature stand-in for R's C API (tests/rmock; tests/test_rshim_cpu.py, tests/test_gpu_rshim.py) -- it has not met
+ * a real R yet.  It is the binding a maintainer adds to put the B200 path behind the unchanged haystack() API
+ * (package skeleton in rshim/).  Rules it follows:
  *   - REAL()/INTEGER() pointers go straight through: R matrices are column-major doubles, dgRMatrix
  *     slots are @p int, @j int (0-based), @x double -- exactly what the C ABI takes.
  *   - outputs are allocated with allocVector under PROTECT;

@@ -54,6 +54,8 @@ SIGNATURES = {
     "hs_dkl_dense_dev": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_dkl_perm_dense_dev": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "hs_density_dev": (_int, [_vp, _vp, _i64, _int, _vp, _int, _vp, _vp, _vp]),
+    "hs_profile_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp]),
+    "hs_profile_dense": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_row_stats_csr": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _vp, _vp]),
     "hs_row_stats_csr_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "hs_csc_to_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),

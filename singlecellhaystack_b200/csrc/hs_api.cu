@@ -307,7 +307,7 @@ void hs_destroy(hs_ctx* ctx) {
                     &ctx->dens64, &ctx->xin, &ctx->gin, &ctx->win, &ctx->part, &ctx->out,
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
                     &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals, &ctx->perm_gp, &ctx->out_rand,
-                    &ctx->tile_ent, &ctx->tile_ws, &ctx->conv_cp, &ctx->conv_ri, &ctx->conv_x, &ctx->conv_p, &ctx->conv_j, &ctx->conv_xo};
+                    &ctx->tile_ent, &ctx->tile_ws, &ctx->prof_x, &ctx->prof_out, &ctx->conv_cp, &ctx->conv_ri, &ctx->conv_x, &ctx->conv_p, &ctx->conv_j, &ctx->conv_xo};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int k = 0; k < hs_ctx::kRing; ++k) {
@@ -1095,6 +1095,61 @@ int hs_dkl_dense_dev(hs_ctx* ctx, const float* expr_dev, int64_t n_genes, int64_
   ScopedTimer tm(ctx, HS_T_DENSE);
   HS_TRY(hs_run_dense_f32(ctx, expr_dev, n_genes, ld, dkl_dev_out));
   tm.stop();
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+// ---- prepare_clustering (R/haystack_continuous.R:604-666): gene x grid profiles, rows summing to 1 ----
+// Not a hot path (a few hundred selected genes): plain synchronous uploads.
+int hs_profile_csr(hs_ctx* ctx, const void* p, int p_is_64, const int32_t* j, const double* x, int64_t n_genes,
+                   double* profile_out) {
+  try {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || !p || !profile_out) return hs_fail(ctx, HS_ERR_INVALID, "hs_profile_csr: bad arguments");
+  if (n_genes == 0) return HS_OK;
+  std::vector<int64_t> hp((size_t)n_genes + 1);
+  for (int64_t i = 0; i <= n_genes; ++i) hp[i] = p_is_64 ? ((const int64_t*)p)[i] : (int64_t)((const int32_t*)p)[i];
+  for (int64_t i = 0; i < n_genes; ++i)
+    if (hp[i + 1] < hp[i]) return hs_fail(ctx, HS_ERR_INVALID, "hs_profile_csr: row pointers must be non-decreasing");
+  const int64_t v0 = hp[0], nnz = hp[n_genes] - v0;
+  if (nnz > 0 && (!j || !x)) return hs_fail(ctx, HS_ERR_INVALID, "hs_profile_csr: j/x are NULL");
+  for (auto& v : hp) v -= v0;
+  cudaStream_t st = ctx->stream;
+  HS_TRY(hs_ensure(ctx, ctx->ptrs, sizeof(int64_t) * (size_t)(n_genes + 1)));
+  HS_TRY(hs_ensure(ctx, ctx->cols32, sizeof(int32_t) * (size_t)hs_max<int64_t>(nnz, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->prof_x, sizeof(double) * (size_t)hs_max<int64_t>(nnz, 1)));
+  HS_TRY(hs_ensure(ctx, ctx->prof_out, sizeof(double) * (size_t)n_genes * ctx->G));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->ptrs.p, hp.data(), sizeof(int64_t) * (size_t)(n_genes + 1), cudaMemcpyHostToDevice, st));
+  if (nnz > 0) {
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->cols32.p, j + v0, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->prof_x.p, x + v0, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, st));
+  }
+  HS_TRY(hs_run_profile(ctx, false, (const int64_t*)ctx->ptrs.p, (const int32_t*)ctx->cols32.p, (const double*)ctx->prof_x.p, 0,
+                        n_genes, (double*)ctx->prof_out.p));
+  HS_CUDA(ctx, cudaMemcpyAsync(profile_out, ctx->prof_out.p, sizeof(double) * (size_t)n_genes * ctx->G, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_profile_dense(hs_ctx* ctx, const double* expr, int64_t n_genes, int64_t ld, double* profile_out) {
+  try {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_genes < 0 || ld < n_genes || !profile_out || (n_genes > 0 && !expr))
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_profile_dense: bad arguments");
+  if (n_genes == 0) return HS_OK;
+  const int64_t N = ctx->N;
+  cudaStream_t st = ctx->stream;
+  HS_TRY(hs_ensure(ctx, ctx->prof_x, sizeof(double) * (size_t)n_genes * N));
+  HS_TRY(hs_ensure(ctx, ctx->prof_out, sizeof(double) * (size_t)n_genes * ctx->G));
+  HS_CUDA(ctx, cudaMemcpy2DAsync(ctx->prof_x.p, sizeof(double) * n_genes, expr, sizeof(double) * ld, sizeof(double) * n_genes,
+                                 (size_t)N, cudaMemcpyHostToDevice, st));
+  HS_TRY(hs_run_profile(ctx, true, nullptr, nullptr, (const double*)ctx->prof_x.p, n_genes, n_genes, (double*)ctx->prof_out.p));
+  HS_CUDA(ctx, cudaMemcpyAsync(profile_out, ctx->prof_out.p, sizeof(double) * (size_t)n_genes * ctx->G, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
   return HS_OK;
   } HS_ABI_CATCH(ctx)
 }

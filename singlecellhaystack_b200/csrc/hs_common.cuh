@@ -70,6 +70,7 @@ struct hs_ctx {
   DevBuf dtile_hi, dtile_lo;   // fp16 hi / lo density operands pre-tiled for the tensor-core kernels
   bool tiles_valid = false;    // the tiles match the resident density matrix
   DevBuf umma_flags;
+  DevBuf prof_x, prof_out;     // hs_profile_*: uploaded fp64 values, gene x grid result
   DevBuf tile_ent, tile_ws;    // tile path of the sparse contraction: tile-major entries, cuts / region / tile tables
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, (id, value) pairs, values of the selected rows
@@ -162,6 +163,8 @@ int hs_run_dense_umma(hs_ctx* ctx, bool perm, const float* e_dev, int64_t ld, co
                       const int32_t* perm_dev, int index_base, int64_t n_rows, double* out_dev,
                       const int** flag_dev_out);
 bool hs_umma_disabled();   // HS_DISABLE_UMMA=1 forces the SIMT kernels (A/B comparisons)
+int hs_run_profile(hs_ctx* ctx, bool dense, const int64_t* p_dev, const int32_t* j_dev, const double* x_dev, int64_t ld,
+                   int64_t n_rows, double* out_dev);
 int hs_run_dense_f32(hs_ctx* ctx, const float* e_dev, int64_t n_genes, int64_t ld, double* out_dev);
 int hs_run_perm_dense(hs_ctx* ctx, const float* v_dev, const int32_t* perm_dev, int n_perm,
                       int index_base, double* out_dev);

@@ -93,6 +93,75 @@ k_rows_gather_kl(const int64_t* __restrict__ ptr, const int32_t* __restrict__ co
 }
 
 // =================================================================================================
+// prepare_clustering (R/haystack_continuous.R:604-666): the same per-gene column sums, returned as a gene x grid
+// matrix with every row rescaled to sum to 1 (:664) instead of being reduced to D_KL.  One warp per row; the values
+// stay fp64 (as the host hands them over), products are fp32 FMAs in partials of 32 folded into fp64.
+//   CSR  : row r owns cols / vals [ptr[r], ptr[r+1])          (extract_row_dgRMatrix, R/sparse.R:28-37)
+//   dense: E[row + cell * ld]                                  (:647)
+// out is n_rows x G column-major (an R matrix).
+// =================================================================================================
+template <int NACC, bool DENSE>
+__global__ void __launch_bounds__(256)
+k_rows_profile(const int64_t* __restrict__ ptr, const int32_t* __restrict__ cols, const double* __restrict__ vals,
+               int64_t ld, int64_t n_rows, const float* __restrict__ D, int ldD, int G, int64_t n_cells,
+               double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int64_t g0 = DENSE ? 0 : ptr[row];
+    const int64_t nnz = DENSE ? n_cells : ptr[row + 1] - g0;
+    double acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    for (int64_t base = 0; base < nnz; base += 32) {
+      const int cnt = (int)hs_min<int64_t>(32, nnz - base);
+      int64_t myc = 0;
+      float myv = 0.f;
+      if (lane < cnt) {
+        if (DENSE) {
+          myc = base + lane;
+          myv = (float)vals[row + myc * ld];
+        } else {
+          myc = cols[g0 + base + lane];
+          myv = (float)vals[g0 + base + lane];
+          if (myc < 0 || myc >= n_cells) {      // cannot be dereferenced: poison the row
+            myc = 0;
+            myv = __int_as_float(0x7fc00000);
+          }
+        }
+      }
+      float part[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) part[a] = 0.f;
+      for (int t = 0; t < cnt; ++t) {
+        const int64_t c = __shfl_sync(0xffffffffu, myc, t);
+        const float v = __shfl_sync(0xffffffffu, myv, t);
+        if (DENSE && v == 0.f) continue;       // warp-uniform: zeros of a dense row add nothing
+        const float* drow = D + c * ldD;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          const int j = lane + 32 * a;
+          part[a] = fmaf(v, (j < G) ? __ldg(drow + j) : 0.f, part[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] += (double)part[a];
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+      if (lane + 32 * a < G) s += acc[a];
+    s = hs_warp_sum(s);
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) {
+      const int j = lane + 32 * a;
+      if (j < G) out[row + (int64_t)j * n_rows] = acc[a] / s;      // densities / rowSums(densities), :664
+    }
+  }
+}
+
+// =================================================================================================
 // K2 / K4-dense: register-tiled fp32 contraction over cells with split-K partials in fp64.
 // A(row, cell): dense  -> E[row + cell * ld]                       (R matrix, genes x cells)
 //               perm   -> v[perm[cell + row * N] - base]           (sample(x = v), :259)
@@ -310,6 +379,30 @@ int launch_dense(hs_ctx* ctx, const TE* E, int64_t ld, const float* v, const int
 }
 
 }  // namespace
+
+int hs_run_profile(hs_ctx* ctx, bool dense, const int64_t* p_dev, const int32_t* j_dev, const double* x_dev, int64_t ld,
+                   int64_t n_rows, double* out_dev) {
+  if (n_rows <= 0) return HS_OK;
+  const int G = ctx->G;
+  const int nacc = (G + 31) / 32;
+  const int blocks = (int)hs_min<int64_t>((n_rows + 7) / 8, (int64_t)ctx->sm_count * 8);
+  const float* D = (const float*)ctx->D32.p;
+#define HS_PROFILE(NA)                                                                                              \
+  do {                                                                                                              \
+    if (dense) k_rows_profile<NA, true><<<blocks, 256, 0, ctx->stream>>>(p_dev, j_dev, x_dev, ld, n_rows, D, ctx->ldD, G, ctx->N, out_dev); \
+    else k_rows_profile<NA, false><<<blocks, 256, 0, ctx->stream>>>(p_dev, j_dev, x_dev, ld, n_rows, D, ctx->ldD, G, ctx->N, out_dev);     \
+  } while (0)
+  if (nacc <= 1) HS_PROFILE(1);
+  else if (nacc <= 2) HS_PROFILE(2);
+  else if (nacc <= 4) HS_PROFILE(4);
+  else if (nacc <= 8) HS_PROFILE(8);
+  else if (nacc <= 16) HS_PROFILE(16);
+  else if (nacc <= 32) HS_PROFILE(32);
+  else return hs_fail(ctx, HS_ERR_INVALID, "grid.points=%d exceeds the supported maximum of 1024", G);
+#undef HS_PROFILE
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}
 
 int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const float* x_dev, int64_t n_rows,
                double* out_dev) {

@@ -324,6 +324,29 @@ class DeviceContext:
         self._check(self._lib.hs_dkl_csr(self._h, _ptr(p), is64, _ptr(j), _ptr(x), m, _ptr(out)), "hs_dkl_csr")
         return out
 
+    # -- prepare_clustering (R/haystack_continuous.R:604-666) ---------------------------------
+    def profile_csr(self, p, j, x) -> np.ndarray:
+        """hs_profile_csr: (M, G) matrix of per-gene column sums colSums(D[ind,] * val), rows rescaled to sum to 1."""
+        p = np.ascontiguousarray(p)
+        if p.dtype not in (np.int32, np.int64):
+            p = p.astype(np.int64)
+        j = np.ascontiguousarray(j, dtype=np.int32)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        m = p.size - 1
+        out = np.empty((m, self.shape[1]), dtype=np.float64, order="F")
+        self._check(self._lib.hs_profile_csr(self._h, _ptr(p), int(p.dtype == np.int64), _ptr(j), _ptr(x), m, _ptr(out)),
+                    "hs_profile_csr")
+        return out
+
+    def profile_dense(self, expression) -> np.ndarray:
+        e = _f64_colmajor(expression, "expression")
+        if e.ndim != 2 or e.shape[1] != self.shape[0]:
+            raise ValueError("The number of columns in 'expression' must be the same as the rows in 'x'")
+        m = e.shape[0]
+        out = np.empty((m, self.shape[1]), dtype=np.float64, order="F")
+        self._check(self._lib.hs_profile_dense(self._h, _ptr(e), m, m, _ptr(out)), "hs_profile_dense")
+        return out
+
     # -- K4 -----------------------------------------------------------------------------------
     def dkl_perm_dense(self, v, perm, index_base=1) -> np.ndarray:
         """v (N,), perm (N, R) column r = sample.int(N).  Returns (R,)."""
