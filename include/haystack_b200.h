@@ -238,6 +238,24 @@ int hs_csc_to_csr_dev(hs_ctx* ctx, const int64_t* cp_dev, const int32_t* ri_dev,
                       int64_t n_rows, int64_t n_cols, int64_t* p_out_dev, int32_t* j_out_dev,
                       float* x_out_dev);
 
+/* ---- R-compatible host helpers (no GPU involved; optional) --------------------------------- */
+/* For hosts WITHOUT R that want R's draws: set.seed(seed) followed by unif_rand() / sample.int() / kmeans() of base R
+ * (Mersenne-Twister; sample.kind "Rejection" as in R >= 3.6.0, or "Rounding" when sample_kind_rounding != 0).
+ * With them the Python host layer replays `set.seed(1234); haystack(dat.tsne, dat.expression)` and reproduces the
+ * reference's printed vignette table on the B200 (tests/test_gpu_r_parity.py).  The R shim does not use them: under
+ * R the draws are R's own (R/haystack_continuous.R:259, :275, :437; R/haystack_highD.R:83, :95, :110). */
+typedef struct hs_rng hs_rng;
+int hs_r_rng_create(uint32_t seed, int sample_kind_rounding, hs_rng** out);
+void hs_r_rng_destroy(hs_rng* rng);
+double hs_r_unif_rand(hs_rng* rng);
+/* `count` consecutive sample.int(n, size) draws (1-based ids), one after the other in ids_out. */
+int hs_r_sample_int(hs_rng* rng, int32_t n, int32_t size, int32_t count, int32_t* ids_out);
+/* sample(n, 1, prob = prob): one 1-based id. */
+int hs_r_sample_prob_one(hs_rng* rng, int32_t n, const double* prob, int32_t* id_out);
+/* kmeans(x, centers = k, iter.max, nstart)$centers, Hartigan-Wong; x: m x d column-major, centers_out: k x d. */
+int hs_r_kmeans(hs_rng* rng, const double* x, int32_t m, int32_t d, int32_t k, int32_t iter_max, int32_t nstart,
+                double* centers_out, double* tot_withinss_out, int32_t* ifault_out);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Number of kernels of this library launched on this context since creation. */
 int64_t hs_launch_count(const hs_ctx* ctx);

@@ -60,6 +60,12 @@ SIGNATURES = {
     "hs_row_stats_csr_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
     "hs_csc_to_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hs_csc_to_csr_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
+    "hs_r_rng_create": (_int, [C.c_uint32, _int, C.POINTER(_vp)]),
+    "hs_r_rng_destroy": (None, [_vp]),
+    "hs_r_unif_rand": (C.c_double, [_vp]),
+    "hs_r_sample_int": (_int, [_vp, _i32, _i32, _i32, _vp]),
+    "hs_r_sample_prob_one": (_int, [_vp, _i32, _vp, _vp]),
+    "hs_r_kmeans": (_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "hs_launch_count": (_i64, [_vp]),
     "hs_last_timers": (_int, [_vp, C.POINTER(C.c_float), _int]),
     "hs_enable_timers": (_int, [_vp, _int]),

@@ -2,9 +2,10 @@
 
 This stays on the HOST in the drop-in design: it draws random numbers, and
 under R it is R's own `kmeans()` / `sample()` that run, so `set.seed()` reproducibility is R's.
-This Python mirror exists so the package is usable without R; its random stream is numpy's and
-its "centroid" method is Lloyd's algorithm, not R's Hartigan-Wong -- results agree in
-distribution, not bit for bit.  Parity tests therefore always pass `grid_coord` explicitly.
+This Python mirror exists so the package is usable without R.  With `rng=rcompat.RRandom(seed)` it is R's
+own procedure -- kmeans() as Hartigan-Wong with nstart restarts on R's Mersenne-Twister stream, sample() for the
+seeding method -- and returns the grid an R session with set.seed(seed) gets.  With a numpy seed / Generator the
+random stream is numpy's and "centroid" is Lloyd's algorithm: same distribution, different numbers.
 """
 from __future__ import annotations
 
@@ -64,23 +65,28 @@ def _kmeans_lloyd(x: np.ndarray, k: int, iter_max: int, nstart: int, rng: np.ran
 def get_grid_points(input, method: str = "centroid", grid_points: int = 100, rng=None) -> np.ndarray:
     """R/haystack_highD.R:72-134.  Returns (grid.points, d) coordinates."""
     x = np.asarray(input, dtype=np.float64)
-    rng = np.random.default_rng(rng)
+    r_stream = rng if hasattr(rng, "kmeans") and hasattr(rng, "sample_prob_one") else None     # rcompat.RRandom
+    if r_stream is None:
+        rng = np.random.default_rng(rng)
     if x.shape[0] < grid_points:                                                      # :74-77
         warnings.warn(f"Fewer input points than grid.points. Adjusting value of grid.points to {x.shape[0]}")
         grid_points = x.shape[0]
     if method == "centroid":                                                          # :79-85
+        if r_stream is not None:           # R's own kmeans(): Hartigan-Wong on R's random stream
+            return r_stream.kmeans(x, int(grid_points), iter_max=10, nstart=10)
         return _kmeans_lloyd(x, int(grid_points), iter_max=10, nstart=10, rng=rng)
     if method == "seeding":                                                           # :87-129
         n, d = x.shape
         grid = np.full((grid_points, d), np.nan)
-        index = int(rng.integers(n))                                                  # :95
+        index = int(r_stream.sample_int(n, 1)[0]) - 1 if r_stream is not None else int(rng.integers(n))   # :95
         grid[0] = x[index]
         min_dist = get_dist_two_sets(x, grid[0:1])[:, 0]
         dist_to_grid = np.full((n, grid_points), np.nan)
         dist_to_grid[:, 0] = min_dist
         for i in range(1, grid_points):
             probs = min_dist ** 2                                                     # :107
-            index = int(rng.choice(n, p=probs / probs.sum()))                         # :110
+            index = (r_stream.sample_prob_one(probs) - 1 if r_stream is not None
+                     else int(rng.choice(n, p=probs / probs.sum())))                  # :110
             grid[i] = x[index]
             tmp = get_dist_two_sets(x, grid[i:i + 1])[:, 0]
             dist_to_grid[:, i] = tmp

@@ -156,7 +156,8 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
     (R/haystack_continuous.R:27-339).  Positional / keyword arguments up to `spline_method` are the
     reference's; the keyword-only ones are host plumbing:
       gene_names   row names of `expression` (R takes them from rownames())
-      rng          seed or numpy Generator for every random draw (R: set.seed())
+      rng          seed or numpy Generator for every random draw (R: set.seed()); or rcompat.RRandom(seed): R's own
+                   stream -- grid, randomizations and folds are then what R draws after set.seed(seed)
       perm_source  callable(kind, gene0, n, size, count) -> (count, size) 1-based ids, replaces sample();
                    or the string "device": the draws are made on the GPU from a seed taken from `rng`
                    (hs_dkl_perm_csr_seeded / hs_dkl_perm_dense_seeded; stream = position in
@@ -291,7 +292,13 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
     if dir_randomization is not None:
         os.makedirs(dir_randomization, exist_ok=True)
 
-    rng = np.random.default_rng(rng)
+    # rng = rcompat.RRandom(seed): every draw below is R's, in R's order (grid -> randomizations gene-major -> folds of
+    # the mean model -> folds of the sd model): the call replays set.seed(seed); haystack(...)
+    r_stream = rng if hasattr(rng, "perm_source") and hasattr(rng, "folds") else None
+    if r_stream is None:
+        rng = np.random.default_rng(rng)
+    elif perm_source is None:
+        perm_source = r_stream.perm_source
     if grid_coord is None:
         _message(verbose, "### deciding grid points...")
         grid_coord = _grid.get_grid_points(x, method=grid_method, grid_points=int(grid_points), rng=rng)
@@ -320,7 +327,7 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         all_D_KL_randomized = np.full((n_genes_to_randomize, randomization_count), np.nan)
 
         if sparse_in and device_draw:
-            perm_seed = int(rng.integers(0, 2 ** 63))
+            perm_seed = int(r_stream.unif_rand() * 2 ** 53) if r_stream is not None else int(rng.integers(0, 2 ** 63))
             _message(verbose, "### performing randomizations...")
             D_KL_observed, rand = ctx.dkl_csr_randomized(expression.p, expression.j, expression.x, genes_to_randomize,
                                                          randomization_count, perm_seed)
@@ -358,7 +365,7 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
                     flush()
             flush()
         elif device_draw:
-            perm_seed = int(rng.integers(0, 2 ** 63))
+            perm_seed = int(r_stream.unif_rand() * 2 ** 53) if r_stream is not None else int(rng.integers(0, 2 ** 63))
             for i, g in enumerate(genes_to_randomize):
                 all_D_KL_randomized[i, :] = ctx.dkl_perm_dense_seeded(expression[int(g)], randomization_count, perm_seed,
                                                                       stream_base=i * randomization_count)
@@ -377,9 +384,12 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
     _message(verbose, "### estimating p-values...")
     names_rand = [gene_names[int(g)] for g in genes_to_randomize] if gene_names is not None else None
     sets_mean, sets_sd = cv_folds if cv_folds is not None else (None, None)
+    if r_stream is not None and cv_folds is None:
+        sets_mean = r_stream.folds(n_genes_to_randomize)
+        sets_sd = r_stream.folds(n_genes_to_randomize)
     pv = _fit.get_log_p_D_KL_continuous(D_KL_observed, all_D_KL_randomized, coeffVar, coeffVar[genes_to_randomize],
                                         spline_method=spline_method, sets_mean=sets_mean, sets_sd=sets_sd,
-                                        rng=rng, names=names_rand, verbose=verbose)
+                                        rng=None if r_stream is not None else rng, names=names_rand, verbose=verbose)
     rand_info = pv["info"]
     rand_info["method"] = spline_method
     rand_info["genes_to_randomize"] = genes_to_randomize + 1          # 1-based, as R stores them

@@ -73,3 +73,23 @@ def test_vignette_call_on_the_device(ctx, toy, sparse):
         np.testing.assert_allclose(r["log.p.vals"].values, z["log_p_vals"], atol=1e-3)
         top = hh.show_result_haystack(res, n=10)
         assert list(top.index) == [t[0] for t in VIGNETTE_TOP10]
+
+
+def test_product_alone_replays_the_r_session(ctx, toy):
+    """No oracle in the loop: haystack(rng = RRandom(1234)) draws the grid (Hartigan-Wong k-means), the 100 x 100
+    permutations and the folds from R's stream inside the product and scores on the B200; the top-10 table is the one
+    the reference printed."""
+    from singlecellhaystack_b200.rcompat import RRandom
+    coord, expr = toy["coord"].astype(np.float64), toy["expression"].astype(np.float64)
+    names = [str(s) for s in toy["gene_names"]]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = hh.haystack(coord, expr, rng=RRandom(1234), ctx=ctx, gene_names=names, verbose=False)
+    r = res["results"]
+    for gene, dkl, logp, padj in VIGNETTE_TOP10:
+        assert abs(r.loc[gene, "D_KL"] - dkl) <= 1e-5 * dkl + 5.1e-7
+        assert abs(r.loc[gene, "log.p.vals"] - logp) <= 1e-3
+        assert abs(r.loc[gene, "log.p.adj"] - padj) <= 1e-3
+    assert list(hh.show_result_haystack(res, n=10).index) == [t[0] for t in VIGNETTE_TOP10]
+    cv = res["info"]["randomization"]
+    assert (cv["mean"]["cv.selected"]["df"], cv["sd"]["cv.selected"]["df"]) == (3, 5) if "cv.selected" in cv.get("mean", {}) else True
