@@ -12,7 +12,8 @@
 namespace {
 
 constexpr int kCellsPerBlock = 128;
-constexpr int kJT = 4;  // grid points per register tile in the distance kernel
+constexpr int kJT = 8;  // grid points per register tile in the distance kernel: one x load feeds 8 independent
+                        // (subtract, fused multiply-add) chains
 
 // ---- squared distances, per-cell minimum and nearest grid point --------------------------------
 // x: [N x d] column-major, grid: [G x d] column-major.  sq: [G][N] (column-major N x G, like R's
@@ -139,9 +140,11 @@ __global__ void __launch_bounds__(kCellsPerBlock)
 k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, int64_t c_lo, int64_t c_hi,
           const double* __restrict__ bw_dev, const double* __restrict__ wq, float* __restrict__ D32,
           double* __restrict__ dens64, double* __restrict__ qpart) {
-  extern __shared__ unsigned char smem_raw[];
-  float* tile = reinterpret_cast<float*>(smem_raw);                               // [128][129]
-  double* qs = reinterpret_cast<double*>(smem_raw + sizeof(float) * 128 * 129 + 8); // [4][128]
+  // 32 grid columns per pass: 17 KB of shared memory per block (a 128-column tile allowed only 3 blocks per SM,
+  // too few warps to hide the latency of the fp64 exp / sqrt / divide chains)
+  constexpr int kW = 32;
+  __shared__ float tile[kCellsPerBlock][kW + 1];
+  __shared__ double qs[4][kW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t c = c_lo + (int64_t)blockIdx.x * kCellsPerBlock + tid;
   const bool valid = c < c_hi;
@@ -149,9 +152,9 @@ k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, int64_t c_lo
   const int64_t gblock = c_lo / kCellsPerBlock + blockIdx.x;      // block number among all cells
   const double bw = *bw_dev;
   const double w = (valid && wq) ? wq[c] : 1.0;
-  for (int j0 = 0; j0 < ldD; j0 += 128) {
-    const int jn = max(0, min(128, G - j0));        // real columns in this chunk
-    const int jpad = min(128, ldD - j0);            // columns to store (zero padded)
+  for (int j0 = 0; j0 < ldD; j0 += kW) {
+    const int jn = max(0, min(kW, G - j0));        // real columns in this chunk
+    const int jpad = min(kW, ldD - j0);            // columns to store (zero padded)
     for (int jj = 0; jj < jn; ++jj) {
       double dv = 0.0;
       if (valid) {
@@ -160,18 +163,16 @@ k_density(const double* __restrict__ sq, int64_t N, int G, int ldD, int64_t c_lo
         dv = exp(-dn * dn / 2);                     // :176-177
         if (dens64) dens64[(int64_t)(j0 + jj) * N + c] = dv;
       }
-      tile[tid * 129 + jj] = (float)dv;
+      tile[tid][jj] = (float)dv;
       const double qsum = hs_warp_sum(valid ? dv * w : 0.0);   // :180 / :182
-      if (lane == 0) qs[warp * 128 + jj] = qsum;
+      if (lane == 0) qs[warp][jj] = qsum;
     }
-    for (int jj = jn; jj < jpad; ++jj) tile[tid * 129 + jj] = 0.f;
+    for (int jj = jn; jj < jpad; ++jj) tile[tid][jj] = 0.f;
     __syncthreads();
-    for (int jj = tid; jj < jn; jj += kCellsPerBlock)
-      qpart[gblock * G + j0 + jj] = (qs[jj] + qs[128 + jj]) + (qs[256 + jj] + qs[384 + jj]);
+    if (tid < jn) qpart[gblock * G + j0 + tid] = (qs[0][tid] + qs[1][tid]) + (qs[2][tid] + qs[3][tid]);
     for (int r = warp; r < kCellsPerBlock; r += 4) {
       const int64_t cr = c_lo + (int64_t)blockIdx.x * kCellsPerBlock + r;
-      if (cr < c_hi)
-        for (int jj = lane; jj < jpad; jj += 32) D32[cr * ldD + j0 + jj] = tile[r * 129 + jj];
+      if (cr < c_hi && lane < jpad) D32[cr * ldD + j0 + lane] = tile[r][lane];
     }
     __syncthreads();
   }
@@ -287,10 +288,8 @@ int hs_density_step_dens(hs_ctx* ctx, int64_t N, int G, const double* wq_dev, in
   const int64_t n_loc = hs_max<int64_t>(c_hi - c_lo, 0);
   if (want_dens64) HS_TRY(hs_ensure(ctx, ctx->dens64, sizeof(double) * (size_t)N * G));
   if (n_loc > 0) {
-    const size_t smem2 = sizeof(float) * 128 * 129 + 8 + sizeof(double) * 4 * 128;
-    HS_CUDA(ctx, cudaFuncSetAttribute(k_density, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     const int nb = (int)((n_loc + kCellsPerBlock - 1) / kCellsPerBlock);
-    k_density<<<nb, kCellsPerBlock, smem2, st>>>((const double*)ctx->sq.p, N, G, ldD, c_lo, c_hi, bw_dev, wq_dev,
+    k_density<<<nb, kCellsPerBlock, 0, st>>>((const double*)ctx->sq.p, N, G, ldD, c_lo, c_hi, bw_dev, wq_dev,
                                                   (float*)ctx->D32.p, want_dens64 ? (double*)ctx->dens64.p : nullptr,
                                                   (double*)ctx->qpart.p);
     HS_LAUNCH_CHECK(ctx);
