@@ -1049,6 +1049,95 @@ bool hs_tile_path_enabled(const hs_ctx* ctx) {
   return !hs_umma_disabled();
 }
 
+// Launch the MMA kernel over prepared tiles (entries / tile_start / tile_cnt) and the fused KL epilogue.
+static int launch_tile_mma(hs_ctx* ctx, const uint2* entries, const unsigned long long* tile_start, const uint32_t* tile_cnt,
+                           unsigned int* pair_done, const int32_t* sorted_rows_dev, int64_t n_rows, int npad, double* out_dev,
+                           int out_n_perm, int64_t out_n_sel, const int* flags, cudaEvent_t* ev, bool dbg) {
+  cudaStream_t st = ctx->stream;
+  const int G = ctx->G;
+  const int n_tr = (int)((n_rows + kTM - 1) / kTM);
+  const int n_pairs = (n_tr + 1) / 2;
+  const int n_slabs = (int)((ctx->N + kSlab - 1) / kSlab);
+  // ---- step 2: MMA ----
+  // cell segments: enough CTAs for ~8 waves (the tail is then one short CTA), at least 64 stages each;
+  // blockIdx runs over the pairs first, so the CTAs in flight share a segment's density tiles through L2
+  int form = 1;      // 1: one tile row per CTA, three stages (k_tile_mma1); 2: two tile rows per CTA (k_tile_mma)
+  if (const char* e = getenv("HS_TILE_FORM")) form = atoi(e) == 2 ? 2 : 1;
+  const int n_units = form == 1 ? n_tr : n_pairs;
+  int64_t want_seg = ((int64_t)ctx->sm_count * 8 + n_units - 1) / n_units;
+  if (const char* e = getenv("HS_TILE_SEGMENTS")) want_seg = hs_max(1, atoi(e));
+  int n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(want_seg, n_slabs / 64));
+  int slabs_per_seg = (n_slabs + n_seg - 1) / n_seg;
+  slabs_per_seg = (slabs_per_seg + kFlushStages - 1) / kFlushStages * kFlushStages;
+  n_seg = (n_slabs + slabs_per_seg - 1) / slabs_per_seg;
+  const int ldP = npad;
+  const int64_t seg_stride = (int64_t)n_pairs * 2 * kTM * ldP;
+  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_seg * (size_t)seg_stride));
+  HS_CUDA(ctx, cudaMemsetAsync(pair_done, 0, (size_t)n_tr * 4, st));
+
+  TileMmaParams prm;
+  prm.entries = entries;
+  prm.tile_start = tile_start;
+  prm.tile_cnt = tile_cnt;
+  prm.sorted_rows = sorted_rows_dev;
+  prm.n_rows = n_rows;
+  prm.n_tr = n_tr;
+  prm.n_pairs = n_pairs;
+  prm.n_slabs = n_slabs;
+  prm.slabs_per_seg = slabs_per_seg;
+  prm.n_seg = n_seg;
+  prm.Dh = (const unsigned char*)ctx->dtile_hi.p;
+  prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
+  prm.P64 = (double*)ctx->part.p;
+  prm.seg_stride = seg_stride;
+  prm.ldP = ldP;
+  prm.G = G;
+  prm.npad = npad;
+  prm.Q = (const double*)ctx->Q.p;
+  prm.pair_done = pair_done;
+  prm.out = out_dev;
+  prm.out_n_perm = out_n_perm;
+  prm.out_n_sel = out_n_sel;
+  prm.flags = flags;
+  prm.dbg = nullptr;
+  if (dbg) {
+    HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
+    HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
+    prm.dbg = (long long*)((char*)ctx->umma_flags.p + 64);
+  }
+  {
+    const int units = form == 1 ? n_tr : n_pairs;
+    int tr_dbg = dbg ? atoi(getenv("HS_TILE_DEBUG")) : 0;
+    prm.dbg_block = (n_seg / 2) * units + hs_min(hs_max(tr_dbg, 0), units - 1);      // a middle segment of that tile row
+  }
+  if (form == 1) {
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1));
+    k_tile_mma1<<<(unsigned)(n_tr * n_seg), kMma1Threads, kSmem1, st>>>(prm);
+  } else {
+    HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMma));
+    k_tile_mma<<<(unsigned)(n_pairs * n_seg), kMmaThreads, kSmemMma, st>>>(prm);
+  }
+  HS_LAUNCH_CHECK(ctx);
+  if (dbg) {
+    long long h[16] = {0};
+    cudaEventRecord(ev[3], st);
+    cudaStreamSynchronize(st);
+    float t_cut = 0, t_fill = 0, t_mma = 0;
+    cudaEventElapsedTime(&t_cut, ev[0], ev[1]);
+    cudaEventElapsedTime(&t_fill, ev[1], ev[2]);
+    cudaEventElapsedTime(&t_mma, ev[2], ev[3]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+    fprintf(stderr, "[tile dbg] prepare %.3f ms, fill / generate %.3f ms, mma %.3f ms\n", t_cut, t_fill, t_mma);
+    cudaMemcpy(h, prm.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tile dbg] rows %lld pairs %d seg %d | CTA: %lld clk over %lld stages (%.0f/stage) | loader wait ring_empty %lld | "
+                    "mma wait acc_empty %lld a_full %lld b_full %lld | producer0 wait stage_empty %lld ring_full %lld | "
+                    "producer1 wait stage_empty %lld ring_full %lld\n",
+            (long long)n_rows, n_pairs, n_seg, h[0], h[1], h[1] ? (double)h[0] / (double)h[1] : 0.0, h[2], h[3], h[4], h[5], h[6], h[7],
+            h[8], h[9]);
+  }
+  return HS_OK;
+}
+
 // Rows (ascending cell ids) x resident density matrix -> D_KL on the tensor cores.
 //   sorted_rows_dev: row ids by descending length (n_rows of them); entries of row r at [ptr[r], ptr[r+1]) of
 //   (cols, vals) or of `pairs`; nnz_total: entries of all rows together.
@@ -1121,82 +1210,7 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   HS_LAUNCH_CHECK(ctx);
   if (dbg) cudaEventRecord(ev[2], st);
 
-  // ---- step 2: MMA ----
-  // cell segments: enough CTAs for ~8 waves (the tail is then one short CTA), at least 64 stages each;
-  // blockIdx runs over the pairs first, so the CTAs in flight share a segment's density tiles through L2
-  int form = 1;      // 1: one tile row per CTA, three stages (k_tile_mma1); 2: two tile rows per CTA (k_tile_mma)
-  if (const char* e = getenv("HS_TILE_FORM")) form = atoi(e) == 2 ? 2 : 1;
-  const int n_units = form == 1 ? n_tr : n_pairs;
-  int64_t want_seg = ((int64_t)ctx->sm_count * 8 + n_units - 1) / n_units;
-  if (const char* e = getenv("HS_TILE_SEGMENTS")) want_seg = hs_max(1, atoi(e));
-  int n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(want_seg, n_slabs / 64));
-  int slabs_per_seg = (n_slabs + n_seg - 1) / n_seg;
-  slabs_per_seg = (slabs_per_seg + kFlushStages - 1) / kFlushStages * kFlushStages;
-  n_seg = (n_slabs + slabs_per_seg - 1) / slabs_per_seg;
-  const int ldP = npad;
-  const int64_t seg_stride = (int64_t)n_pairs * 2 * kTM * ldP;
-  HS_TRY(hs_ensure(ctx, ctx->part, sizeof(double) * (size_t)n_seg * (size_t)seg_stride));
-  HS_CUDA(ctx, cudaMemsetAsync(pair_done, 0, (size_t)n_tr * 4, st));
-
-  TileMmaParams prm;
-  prm.entries = (const uint2*)ctx->tile_ent.p;
-  prm.tile_start = tile_start;
-  prm.tile_cnt = tile_cnt;
-  prm.sorted_rows = sorted_rows_dev;
-  prm.n_rows = n_rows;
-  prm.n_tr = n_tr;
-  prm.n_pairs = n_pairs;
-  prm.n_slabs = n_slabs;
-  prm.slabs_per_seg = slabs_per_seg;
-  prm.n_seg = n_seg;
-  prm.Dh = (const unsigned char*)ctx->dtile_hi.p;
-  prm.Dl = (const unsigned char*)ctx->dtile_lo.p;
-  prm.P64 = (double*)ctx->part.p;
-  prm.seg_stride = seg_stride;
-  prm.ldP = ldP;
-  prm.G = G;
-  prm.npad = npad;
-  prm.Q = (const double*)ctx->Q.p;
-  prm.pair_done = pair_done;
-  prm.out = out_dev;
-  prm.out_n_perm = out_n_perm;
-  prm.out_n_sel = out_n_sel;
-  prm.flags = flags;
-  prm.dbg = nullptr;
-  if (dbg) {
-    HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
-    HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
-    prm.dbg = (long long*)((char*)ctx->umma_flags.p + 64);
-  }
-  {
-    const int units = form == 1 ? n_tr : n_pairs;
-    int tr_dbg = dbg ? atoi(getenv("HS_TILE_DEBUG")) : 0;
-    prm.dbg_block = (n_seg / 2) * units + hs_min(hs_max(tr_dbg, 0), units - 1);      // a middle segment of that tile row
-  }
-  if (form == 1) {
-    HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem1));
-    k_tile_mma1<<<(unsigned)(n_tr * n_seg), kMma1Threads, kSmem1, st>>>(prm);
-  } else {
-    HS_CUDA(ctx, cudaFuncSetAttribute(k_tile_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMma));
-    k_tile_mma<<<(unsigned)(n_pairs * n_seg), kMmaThreads, kSmemMma, st>>>(prm);
-  }
-  HS_LAUNCH_CHECK(ctx);
-  if (dbg) {
-    long long h[16] = {0};
-    cudaEventRecord(ev[3], st);
-    cudaStreamSynchronize(st);
-    float t_cut = 0, t_fill = 0, t_mma = 0;
-    cudaEventElapsedTime(&t_cut, ev[0], ev[1]);
-    cudaEventElapsedTime(&t_fill, ev[1], ev[2]);
-    cudaEventElapsedTime(&t_mma, ev[2], ev[3]);
-    for (auto& e : ev) cudaEventDestroy(e);
-    fprintf(stderr, "[tile dbg] cuts+scan %.3f ms, fill %.3f ms, mma %.3f ms\n", t_cut, t_fill, t_mma);
-    cudaMemcpy(h, prm.dbg, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tile dbg] rows %lld pairs %d seg %d | CTA: %lld clk over %lld stages (%.0f/stage) | loader wait ring_empty %lld | "
-                    "mma wait acc_empty %lld a_full %lld b_full %lld | producer0 wait stage_empty %lld ring_full %lld | "
-                    "producer1 wait stage_empty %lld ring_full %lld\n",
-            (long long)n_rows, n_pairs, n_seg, h[0], h[1], h[1] ? (double)h[0] / (double)h[1] : 0.0, h[2], h[3], h[4], h[5], h[6], h[7],
-            h[8], h[9]);
-  }
-  return HS_OK;
+  return launch_tile_mma(ctx, (const uint2*)ctx->tile_ent.p, tile_start, tile_cnt, pair_done, sorted_rows_dev, n_rows, npad, out_dev,
+                         out_n_perm, out_n_sel, flags, ev, dbg);
 }
+
