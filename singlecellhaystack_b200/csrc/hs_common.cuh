@@ -147,6 +147,12 @@ int hs_run_perm_dense_seeded(hs_ctx* ctx, const float* v_dev, int n_perm, uint64
 int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev,
                        const unsigned long long* unit_stream_dev = nullptr);
+int hs_run_perm_tiles(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total, const float* val_dev,
+                      int n_perm, uint64_t seed, uint64_t stream_base, const unsigned long long* unit_stream_dev,
+                      const int32_t* sorted_rows_dev, double* out_dev, int* flags);
+int hs_run_gather_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, const float* val_dev, int64_t n_sel, int n_perm,
+                         uint64_t seed, uint64_t stream_base, const unsigned long long* unit_stream_dev,
+                         const int* run_if_flag, double* out_dev);
 // density stage in shardable steps (hs_density.cu)
 int hs_density_step_dist(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
                          int64_t c_lo, int64_t c_hi, int world);

@@ -92,6 +92,62 @@ k_rows_gather_kl(const int64_t* __restrict__ ptr, const int32_t* __restrict__ co
   }
 }
 
+// Seeded randomization, order-independent form: row (unit s, randomization r) pairs the unit's i-th value with cell
+// pi(i) of the keyed permutation (hs_prp.cuh), evaluated on the fly.  Chained behind the tile path of the seeded entry
+// points (values beyond fp16, an overflowing tile window) and used directly where that path does not apply.
+template <int NACC>
+__global__ void __launch_bounds__(256)
+k_rows_gather_seeded(const int64_t* __restrict__ gp, const float* __restrict__ vals, int64_t n_sel, int n_perm,
+                     unsigned long long seed, unsigned long long stream_base,
+                     const unsigned long long* __restrict__ unit_stream, const float* __restrict__ D, int ldD, int G,
+                     int64_t n_cells, const double* __restrict__ Q, const int* __restrict__ run_if_flag,
+                     double* __restrict__ out) {
+  if (run_if_flag && !(*run_if_flag & 1)) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t n_rows = n_sel * n_perm;
+  for (int64_t row = warp0; row < n_rows; row += nwarps) {
+    const int64_t s = row / n_perm;
+    const int r = (int)(row - s * n_perm);
+    const int64_t g0 = gp[s];
+    const int64_t nnz = hs_min<int64_t>(gp[s + 1] - g0, n_cells);
+    const uint64_t stream = unit_stream ? (uint64_t)unit_stream[s] + (uint64_t)r : (uint64_t)stream_base + (uint64_t)row;
+    const HsPrp prp = hs_prp_make(seed, stream, (uint32_t)n_cells);
+    double acc[NACC];
+#pragma unroll
+    for (int a = 0; a < NACC; ++a) acc[a] = 0.0;
+    for (int64_t base = 0; base < nnz; base += 32) {
+      const int cnt = (int)hs_min<int64_t>(32, nnz - base);
+      uint32_t myc = 0;
+      float myv = 0.f;
+      if (lane < cnt) {
+        myc = hs_prp_forward(prp, (uint32_t)(base + lane));
+        myv = vals[g0 + base + lane];
+      }
+      float part[NACC];
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) part[a] = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < cnt; ++t) {
+        const uint32_t c = __shfl_sync(0xffffffffu, myc, t);
+        const float v = __shfl_sync(0xffffffffu, myv, t);
+        const float* drow = D + (int64_t)c * ldD;
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+          const int j = lane + 32 * a;
+          const float dv = (j < G) ? __ldg(drow + j) : 0.f;
+          part[a] = fmaf(v, dv, part[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NACC; ++a) acc[a] += (double)part[a];
+    }
+    const double kl = hs_kl_epilogue<NACC>(acc, Q, G, lane);
+    if (lane == 0) out[s + (int64_t)r * n_sel] = kl;
+  }
+}
+
 // =================================================================================================
 // prepare_clustering (R/haystack_continuous.R:604-666): the same per-gene column sums, returned as a gene x grid
 // matrix with every row rescaled to sum to 1 (:664) instead of being reduced to D_KL.  One warp per row; the values
@@ -412,6 +468,34 @@ int hs_run_csr(hs_ctx* ctx, const int64_t* p_dev, const int32_t* j_dev, const fl
   const int* flag = nullptr;
   HS_TRY(hs_run_slab_spmm(ctx, false, p_dev, n_rows, 1, j_dev, x_dev, 0, out_dev, 0, 0, /*allow_tiles=*/true, &flag));
   return launch_rows_gather<false>(ctx, p_dev, j_dev, x_dev, n_rows, 1, n_rows, 0, flag, out_dev);
+}
+
+int hs_run_gather_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, const float* val_dev, int64_t n_sel, int n_perm,
+                         uint64_t seed, uint64_t stream_base, const unsigned long long* unit_stream_dev,
+                         const int* run_if_flag, double* out_dev) {
+  const int64_t n_rows = n_sel * (int64_t)n_perm;
+  if (n_rows <= 0) return HS_OK;
+  const int G = ctx->G;
+  const int nacc = (G + 31) / 32;
+  if (nacc > 4) return hs_fail(ctx, HS_ERR_INVALID, "internal: seeded gather is the fallback of the tile path (grid.points <= 128)");
+  const int blocks = (int)hs_min<int64_t>((n_rows + 7) / 8, (int64_t)ctx->sm_count * 8);
+  const float* D = (const float*)ctx->D32.p;
+  const double* Q = (const double*)ctx->Q.p;
+#define HS_SEEDED_CASE(NA)                                                                                              \
+  case NA:                                                                                                              \
+    k_rows_gather_seeded<NA><<<blocks, 256, 0, ctx->stream>>>(gene_ptr_dev, val_dev, n_sel, n_perm, seed, stream_base,    \
+                                                              unit_stream_dev, D, ctx->ldD, G, ctx->N, Q, run_if_flag,   \
+                                                              out_dev);                                                  \
+    break;
+  switch (nacc) {
+    HS_SEEDED_CASE(1)
+    HS_SEEDED_CASE(2)
+    HS_SEEDED_CASE(3)
+    HS_SEEDED_CASE(4)
+  }
+#undef HS_SEEDED_CASE
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
 }
 
 int hs_run_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,

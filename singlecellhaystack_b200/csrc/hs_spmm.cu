@@ -1076,9 +1076,46 @@ int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
   if (hs_slab_cells(ctx) < 4)
     return hs_fail(ctx, HS_ERR_INVALID, "seeded randomization: the density rows do not fit the slab kernel");
   const int64_t n_ids = n_vals_total * n_perm;
+  cudaStream_t st = ctx->stream;
+  // ---- tile path: the draw goes straight into the tensor-core kernel's tiles, one permutation evaluation per stored
+  //      value (hs_tiles.cu: hs_run_perm_tiles); the order-independent gather is chained behind it on the device flag ----
+  bool fused = hs_tile_path_enabled(ctx) && (n_rows + 127) / 128 <= 65535;
+  if (const char* e = getenv("HS_PERM_FUSED")) fused = fused && atoi(e) != 0;
+  if (fused) {
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                              (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_rows, 0, 32, st);
+    const size_t keys_b = ((size_t)n_rows * 4 + 255) & ~(size_t)255;
+    HS_TRY(hs_ensure(ctx, ctx->spmm_ws, 256 + 4 * keys_b + ((cub_bytes + 255) & ~(size_t)255)));
+    char* w = (char*)ctx->spmm_ws.p;
+    int* flags = (int*)w;                    w += 256;
+    uint32_t* keys_in = (uint32_t*)w;        w += keys_b;
+    uint32_t* keys_out = (uint32_t*)w;       w += keys_b;
+    int32_t* rows_in = (int32_t*)w;          w += keys_b;
+    int32_t* rows_out = (int32_t*)w;         w += keys_b;
+    HS_CUDA(ctx, cudaMemsetAsync(flags, 0, 256, st));
+    k_row_len<true><<<(unsigned)((n_rows + 255) / 256), 256, 0, st>>>(gene_ptr_dev, n_rows, n_perm, keys_in, rows_in, flags);
+    HS_LAUNCH_CHECK(ctx);
+    HS_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(w, cub_bytes, keys_in, keys_out, rows_in, rows_out, (int)n_rows,
+                                                           0, 32, st));
+    ctx->launches += 3;
+    int* tile_flag = flags + 2;
+    const int rc = hs_run_perm_tiles(ctx, gene_ptr_dev, n_sel, n_vals_total, val_dev, n_perm, seed, stream_base,
+                                     unit_stream_dev, rows_out, out_dev, tile_flag);
+    if (rc == HS_OK) {
+      if (getenv("HS_PERM_CHECK")) {      // development aid: did the draw hand the call to the gather kernel?
+        int h[4] = {0, 0, 0, 0};
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, flags, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[perm check] rows %lld flags %d %d %d %d\n", (long long)n_rows, h[0], h[1], h[2], h[3]);
+      }
+      return hs_run_gather_seeded(ctx, gene_ptr_dev, val_dev, n_sel, n_perm, seed, stream_base, unit_stream_dev, tile_flag,
+                                  out_dev);
+    }
+    if (rc != -1) return rc;
+  }
   HS_TRY(hs_ensure(ctx, ctx->perm_rp, sizeof(int64_t) * (size_t)(n_rows + 1)));
   HS_TRY(hs_ensure(ctx, ctx->perm_cols, sizeof(uint2) * (size_t)hs_max<int64_t>(n_ids, 1)));   // (cell, value) pairs
-  cudaStream_t st = ctx->stream;
   int64_t* rp = (int64_t*)ctx->perm_rp.p;
   k_perm_row_ptr<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(gene_ptr_dev, n_sel, n_perm, rp);
   HS_LAUNCH_CHECK(ctx);

@@ -37,6 +37,7 @@
 #include <stdlib.h>
 
 #include "hs_common.cuh"
+#include "hs_prp.cuh"
 #include "hs_ptx.cuh"
 
 namespace {
@@ -1040,6 +1041,121 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
   }
 }
 
+
+// =================================================================================================================
+// K4 seeded, drawn straight into the tiles (R/haystack_continuous.R:266-283 with the library's own keyed draw)
+// =================================================================================================================
+// Row (unit s, randomization r) pairs the unit's i-th stored value with cell pi(i), pi the keyed permutation of
+// hs_prp.cuh.  Nothing about a tile depends on the order of its entries (distinct cells per row), so the draw needs no
+// sort: every (tile row, slab) owns a fixed-capacity window of the entry buffer, a counter hands out the places, and
+// the cost is one permutation evaluation per stored value -- proportional to nnz, not to the number of cells.
+//   capacity of a window = mean + 8 sd + 16 of the entries it expects (binomial in the rows' lengths), at most the
+//   128 x 64 a tile can hold; a window that still overflows raises the flag and the call is scored by the chained
+//   gather kernel instead.
+// The rows of one tile row run together (blockIdx order), so a window's sectors fill while they sit in L2.
+
+// per tile row: window capacity and the base of its windows
+__global__ void __launch_bounds__(256)
+k_perm_tile_caps(const int64_t* __restrict__ gp, const int32_t* __restrict__ sorted_rows, int64_t n_rows, int n_perm,
+                 int64_t N, int n_tr, int n_slabs, double sigmas, uint32_t* __restrict__ cap,
+                 unsigned long long* __restrict__ span) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tr) return;
+  double sum = 0.0;
+  for (int r = 0; r < kTM; ++r) {
+    const int64_t pos = (int64_t)t * kTM + r;
+    if (pos >= n_rows) break;
+    const int64_t s = sorted_rows[pos] / n_perm;
+    sum += (double)(gp[s + 1] - gp[s]);
+  }
+  const double mean = sum * (double)kSlab / (double)N;
+  double c = ceil(mean + sigmas * sqrt(mean) + 16.0);
+  c = fmax(fmin(c, (double)(kTM * kSlab)), 2.0);
+  const uint32_t ci = ((uint32_t)c + 1u) & ~1u;
+  cap[t] = ci;
+  span[t] = (unsigned long long)ci * (unsigned long long)n_slabs;
+}
+
+__global__ void __launch_bounds__(1024)
+k_perm_tile_draw(const int64_t* __restrict__ gp, const float* __restrict__ vals, const int32_t* __restrict__ sorted_rows,
+                 int64_t n_rows, int n_perm, uint32_t N, int n_slabs, int n_part, int slabs_per_part, uint64_t seed,
+                 uint64_t stream_base, const unsigned long long* __restrict__ unit_stream,
+                 const uint32_t* __restrict__ cap, const unsigned long long* __restrict__ tbase,
+                 uint32_t* __restrict__ tile_cnt, uint2* __restrict__ entries, int* __restrict__ flags) {
+  // blockIdx = ((tile row * n_part) + part) * 128 + row in tile: the CTAs in flight share one or two (tile row, part)
+  const int rt = (int)(blockIdx.x % kTM);
+  const int64_t grp = blockIdx.x / kTM;
+  const int part = (int)(grp % n_part);
+  const int t = (int)(grp / n_part);
+  const int64_t pos = (int64_t)t * kTM + rt;
+  if (pos >= n_rows) return;
+  const int64_t row = sorted_rows[pos];
+  const int64_t s = row / n_perm;
+  const int64_t g0 = gp[s];
+  const uint32_t nnz = (uint32_t)hs_min<int64_t>(gp[s + 1] - g0, (int64_t)N);
+  const uint64_t stream = unit_stream ? (uint64_t)unit_stream[s] + (uint64_t)(row - s * n_perm) : stream_base + (uint64_t)row;
+  const HsPrp prp = hs_prp_make(seed, stream, N);
+  const uint32_t c_lo = (uint32_t)part * (uint32_t)slabs_per_part * kSlab;
+  const uint32_t c_span = (uint32_t)slabs_per_part * kSlab;
+  const uint32_t wcap = cap[t];
+  uint2* const out = entries + tbase[t];
+  uint32_t* const cnt = tile_cnt + (size_t)t * n_slabs;
+  const uint32_t roff = ((uint32_t)(rt >> 6) << 10) | ((uint32_t)(rt & 7) << 1), c8 = (uint32_t)(rt >> 3) & 7u;
+  const float* v = vals + g0;
+  bool bad = false;
+  // four draws in flight per thread: the counter round trips (an L2 atomic each) overlap
+  constexpr int kU = 4;
+  for (uint32_t i0 = threadIdx.x; i0 < nnz; i0 += kU * blockDim.x) {
+    uint32_t cell[kU], at[kU];
+    float xv[kU];
+    bool ok[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+      ok[u] = i < nnz;
+      cell[u] = hs_prp_enc1(prp, ok[u] ? i : 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      while (cell[u] >= N) cell[u] = hs_prp_enc1(prp, cell[u]);      // cycle walking: rare
+      ok[u] = ok[u] && (cell[u] - c_lo < c_span);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const uint32_t i = i0 + (uint32_t)u * blockDim.x;
+      xv[u] = ok[u] ? __ldg(v + i) : 0.f;
+      at[u] = ok[u] ? atomicAdd(cnt + (cell[u] >> 6), 1u) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (!ok[u]) continue;
+      const uint32_t slab = cell[u] >> 6, k = cell[u] & 63u;
+      const __half h = __float2half_rn(xv[u]);
+      const __half l = __float2half_rn((xv[u] - __half2float(h)) * kLoScale);
+      // beyond fp16, or the window is full: the gather kernel scores the call
+      bad |= !(fabsf(xv[u]) <= 65504.f) || at[u] >= wcap;
+      if (at[u] < wcap) {
+        const uint32_t off = roff | ((k >> 3) << 11) | ((k & 7u) << 7) | (((c8 ^ k) & 7u) << 4);
+        out[(size_t)slab * wcap + at[u]] =
+            make_uint2(off, (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16));
+      }
+    }
+  }
+  if (bad) atomicOr(flags, 1);
+}
+
+// window bases for the MMA kernel; counters of overflowed windows back inside their window
+__global__ void __launch_bounds__(256)
+k_perm_tile_index(const uint32_t* __restrict__ cap, const unsigned long long* __restrict__ tbase, int n_tr, int n_slabs,
+                  unsigned long long* __restrict__ tile_start, uint32_t* __restrict__ tile_cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_tr * n_slabs) return;
+  const int t = (int)(i / n_slabs), sl = (int)(i - (int64_t)t * n_slabs);
+  const uint32_t c = cap[t];
+  tile_start[i] = tbase[t] + (unsigned long long)sl * c;
+  tile_cnt[i] = hs_min(tile_cnt[i], c);
+}
+
 }  // namespace
 
 bool hs_tile_path_enabled(const hs_ctx* ctx) {
@@ -1214,3 +1330,77 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
                          out_n_perm, out_n_sel, flags, ev, dbg);
 }
 
+// Seeded randomization on the tile path: draw into the tiles, multiply.  sorted_rows_dev: the n_sel * n_perm rows
+// (row = unit * n_perm + randomization) by descending length.  Returns -1 when the shape is not for this path; *flags is
+// raised on the device when the call must be scored by the caller's chained fallback instead.
+int hs_run_perm_tiles(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total, const float* val_dev,
+                      int n_perm, uint64_t seed, uint64_t stream_base, const unsigned long long* unit_stream_dev,
+                      const int32_t* sorted_rows_dev, double* out_dev, int* flags) {
+  const int64_t n_rows = n_sel * (int64_t)n_perm;
+  const int64_t N = ctx->N;
+  if (n_rows <= 0) return HS_OK;
+  const int n_tr = (int)((n_rows + kTM - 1) / kTM);
+  const int n_slabs = (int)((N + kSlab - 1) / kSlab);
+  if (!hs_tile_path_enabled(ctx) || N >= ((int64_t)1 << 31) || (int64_t)n_tr * n_slabs > ((int64_t)1 << 31)) return -1;
+  int npad = (ctx->G + 15) & ~15;
+  if (const char* e = getenv("HS_TILE_N128")) {
+    if (*e && *e != '0') npad = 128;
+  }
+  double sigmas = 8.0;
+  if (const char* e = getenv("HS_PERM_TILE_SIGMAS")) sigmas = atof(e);      // tests force the overflow fallback with a negative value
+  // windows: sum_t n_slabs * (mean_t + sigmas * sqrt(mean_t) + 18), bounded with Cauchy-Schwarz from what the host knows
+  const double n_ids = (double)n_vals_total * (double)n_perm;
+  const double mean_sum = n_ids * (double)kSlab / (double)N;
+  const double ent_bound = (double)n_slabs * (mean_sum + fmax(sigmas, 0.0) * sqrt((double)n_tr * mean_sum) + 18.0 * n_tr);
+  const double ent_max = (double)n_tr * (double)n_slabs * (double)(kTM * kSlab);
+  const int64_t ent_cap = (int64_t)(fmin(ent_bound, ent_max) * 1.001) + 4096;
+  HS_TRY(hs_ensure_density_tiles(ctx));
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t cap_b = up((size_t)n_tr * 4), span_b = up((size_t)(n_tr + 1) * 8);
+  const size_t ts_b = up((size_t)n_tr * n_slabs * 8), tc_b = up((size_t)n_tr * n_slabs * 4), pd_b = up((size_t)n_tr * 4);
+  HS_TRY(hs_ensure(ctx, ctx->tile_ws, cap_b + 2 * span_b + ts_b + tc_b + pd_b));
+  HS_TRY(hs_ensure(ctx, ctx->tile_ent, sizeof(uint2) * (size_t)ent_cap));
+  char* w = (char*)ctx->tile_ws.p;
+  uint32_t* cap = (uint32_t*)w;                                w += cap_b;
+  unsigned long long* span = (unsigned long long*)w;           w += span_b;
+  unsigned long long* tbase = (unsigned long long*)w;          w += span_b;
+  unsigned long long* tile_start = (unsigned long long*)w;     w += ts_b;
+  uint32_t* tile_cnt = (uint32_t*)w;                           w += tc_b;
+  unsigned int* pair_done = (unsigned int*)w;
+  cudaStream_t st = ctx->stream;
+
+  // cell ranges (development knob): measured at 1M cells x 10 % fill, cutting the cell axis buys nothing -- the draw is
+  // bound by the L2 request rate (one counter atomic + one 8-byte store per value, ~90 G requests/s), not by partial
+  // sectors reaching DRAM (profiles/r2_perm_tile_draw_raw.csv: 1.5 GB read, 13.9 GB written for 8 GB of entries)
+  int n_part = 1;
+  if (const char* e = getenv("HS_PERM_TILE_PARTS")) n_part = atoi(e);
+  n_part = hs_max(1, hs_min(n_part, n_slabs));
+  const int slabs_per_part = (n_slabs + n_part - 1) / n_part;
+  int threads = (double)n_vals_total / (double)hs_max<int64_t>(n_sel, 1) >= 16384.0 ? 1024 : 256;
+  if (const char* e = getenv("HS_PERM_TILE_THREADS")) threads = hs_max(32, hs_min(1024, atoi(e) / 32 * 32));
+  if ((int64_t)n_tr * n_part * kTM > 0x7fffffffLL) return -1;
+
+  const bool dbg = getenv("HS_TILE_DEBUG") != nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (dbg) {
+    for (auto& e : ev) cudaEventCreate(&e);
+    cudaEventRecord(ev[0], st);
+  }
+  k_perm_tile_caps<<<(n_tr + 255) / 256, 256, 0, st>>>(gene_ptr_dev, sorted_rows_dev, n_rows, n_perm, N, n_tr, n_slabs, sigmas,
+                                                     cap, span);
+  HS_LAUNCH_CHECK(ctx);
+  k_tile_scan<<<1, 1024, 0, st>>>(span, n_tr, tbase);
+  HS_LAUNCH_CHECK(ctx);
+  HS_CUDA(ctx, cudaMemsetAsync(tile_cnt, 0, (size_t)n_tr * n_slabs * 4, st));
+  if (dbg) cudaEventRecord(ev[1], st);
+  k_perm_tile_draw<<<(unsigned)((int64_t)n_tr * n_part * kTM), threads, 0, st>>>(
+      gene_ptr_dev, val_dev, sorted_rows_dev, n_rows, n_perm, (uint32_t)N, n_slabs, n_part, slabs_per_part, seed, stream_base,
+      unit_stream_dev, cap, tbase, tile_cnt, (uint2*)ctx->tile_ent.p, flags);
+  HS_LAUNCH_CHECK(ctx);
+  k_perm_tile_index<<<(unsigned)(((int64_t)n_tr * n_slabs + 255) / 256), 256, 0, st>>>(cap, tbase, n_tr, n_slabs, tile_start,
+                                                                                     tile_cnt);
+  HS_LAUNCH_CHECK(ctx);
+  if (dbg) cudaEventRecord(ev[2], st);
+  return launch_tile_mma(ctx, (const uint2*)ctx->tile_ent.p, tile_start, tile_cnt, pair_done, sorted_rows_dev, n_rows, npad, out_dev,
+                         n_perm, n_sel, flags, ev, dbg);
+}

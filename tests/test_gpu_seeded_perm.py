@@ -109,13 +109,72 @@ def test_short_and_long_row_kernels_agree(ctx, toy):
     xs, _, _ = ho.scale_coords(toy["coord"])
     ctx.density(xs, toy["grid100"])
     vals, _ = _toy_rows(toy, 12)
-    a = ctx.dkl_perm_csr_seeded(vals, 9, 77)
-    os.environ["HS_PERM_SMALL_ROW"] = "0"            # everything through the cell walk
+    os.environ["HS_PERM_FUSED"] = "0"                # the pair generators, not the draw into the tiles
     try:
-        b = ctx.dkl_perm_csr_seeded(vals, 9, 77)
+        a = ctx.dkl_perm_csr_seeded(vals, 9, 77)
+        os.environ["HS_PERM_SMALL_ROW"] = "0"        # everything through the cell walk
+        try:
+            b = ctx.dkl_perm_csr_seeded(vals, 9, 77)
+        finally:
+            del os.environ["HS_PERM_SMALL_ROW"]
     finally:
-        del os.environ["HS_PERM_SMALL_ROW"]
+        del os.environ["HS_PERM_FUSED"]
     np.testing.assert_array_equal(a, b)
+
+
+def _with_env(name, value, fn):
+    import os
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        del os.environ[name]
+
+
+def test_draw_into_tiles_matches_pair_generators(ctx):
+    """The default seeded path draws pi(i) forward, straight into the tensor-core kernel's tiles; the earlier one walks the
+    cells through the inverse permutation, emits sorted pairs and buckets them.  Same rows in the same tiles: the scores
+    are bit-identical, whatever the number of cell ranges the draw is cut into."""
+    n, d, g = 150_000, 5, 100
+    x, _ = synth.make_embedding(n, d, seed=5)
+    xs, _, _ = ho.scale_coords(x)
+    grid = synth.make_grid(xs, g, seed=5)
+    ctx.density(xs, grid)
+    rng = np.random.default_rng(12)
+    vals = [rng.gamma(2.0, 1.0, size=int(k)) for k in (40_000, 1, 0, 15_000, 150_000, 777, 9_000, 31)]
+    n_perm, seed = 40, 99                                  # 320 rows: three tile rows
+    fused = ctx.dkl_perm_csr_seeded(vals, n_perm, seed)
+    pairs = _with_env("HS_PERM_FUSED", "0", lambda: ctx.dkl_perm_csr_seeded(vals, n_perm, seed))
+    np.testing.assert_array_equal(fused, pairs)
+    for parts in ("1", "3", "7"):
+        cut = _with_env("HS_PERM_TILE_PARTS", parts, lambda: ctx.dkl_perm_csr_seeded(vals, n_perm, seed))
+        np.testing.assert_array_equal(fused, cut)
+    # and against the fp64 oracle on a few rows
+    ref = ho.density_stage(xs, grid)
+    pick = [0, 3, 5]
+    inds = [np.stack([po.prp_sample(seed, s * n_perm + r, n, vals[s].size) for r in range(3)]) for s in pick]
+    want = ho.dkl_randomized_sparse([vals[s] for s in pick], inds, ref["density"], ref["Q"])
+    assert _rel(fused[pick][:, :3], want) < RTOL_DKL
+
+
+def test_draw_into_tiles_fallbacks(ctx, toy):
+    """A tile window that overflows, or a value beyond fp16, hands the call to the chained gather kernel on the device."""
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ref = ho.density_stage(xs, toy["grid100"])
+    ctx.density(xs, toy["grid100"])
+    vals, n = _toy_rows(toy, 6)
+    n_perm, seed = 12, 31
+    inds = [np.stack([po.prp_sample(seed, s * n_perm + r, n, v.size) for r in range(n_perm)]) for s, v in enumerate(vals)]
+    want = ho.dkl_randomized_sparse(vals, inds, ref["density"], ref["Q"])
+    normal = ctx.dkl_perm_csr_seeded(vals, n_perm, seed)
+    assert _rel(normal, want) < RTOL_DKL
+    tiny = _with_env("HS_PERM_TILE_SIGMAS", "-1000", lambda: ctx.dkl_perm_csr_seeded(vals, n_perm, seed))   # 2-entry windows
+    assert _rel(tiny, want) < RTOL_DKL
+    assert not np.array_equal(tiny, normal)                # it really took the other kernel
+    big = [v.copy() for v in vals]
+    big[2][0] = 1.0e6
+    want_big = ho.dkl_randomized_sparse(big, inds, ref["density"], ref["Q"])
+    assert _rel(ctx.dkl_perm_csr_seeded(big, n_perm, seed), want_big) < RTOL_DKL
 
 
 @pytest.mark.parametrize("g", [60, 100])
