@@ -62,6 +62,9 @@ struct hs_ctx {
   DevBuf simt_part; // [ksplit][rows][ldP] fp64 split-K partials of the SIMT dense kernel
   DevBuf out;       // fp64 results
   DevBuf stage_j[2], stage_x[2];  // H2D staging (int32 ids, fp64 values)
+  DevBuf bits[2];                 // cell-id bitmaps of a piece of rows (hs_api.cu: packed id upload), double-buffered
+  cudaEvent_t ev_bits[2] = {};    // the bitmaps in bits[k] have been expanded
+  bool bits_used[2] = {};
   DevBuf vals32;    // fp32 values
   DevBuf ptrs;      // int64 row pointers
   DevBuf spmm_ws;   // sparse contraction: flags, sort keys, cub workspace
@@ -136,6 +139,8 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
                        const int** fallback_flag_out);
 int hs_run_csc_to_csr_f32(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const float* x, int64_t n_rows, int64_t n_cols,
                           int64_t nnz, int64_t* p_out, int32_t* j_out, float* x_out);
+int hs_run_bitmap_to_ids(hs_ctx* ctx, const void* bits_dev, int64_t words, const int64_t* ptr_dev, int64_t n_rows,
+                         int32_t* cols_dev, int* flags_dev, cudaStream_t st);
 int hs_run_csc_to_csr_f64(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const double* x, int64_t n_rows, int64_t n_cols,
                           int64_t nnz, int64_t* p_out, int32_t* j_out, double* x_out);
 int hs_run_row_stats_f64(hs_ctx* ctx, const int64_t* p_dev, const double* x_dev, int64_t n_rows, int64_t n_cells,

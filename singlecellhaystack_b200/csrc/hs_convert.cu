@@ -84,6 +84,52 @@ k_csc_scatter(const P* __restrict__ cp, const int32_t* __restrict__ ri, const TI
   }
 }
 
+// ---- cell ids packed as one bit per cell ------------------------------------------------------------------------------
+// The upload of a sparse matrix is bound by PCIe, and at more than ~3 % stored values a row's ascending cell ids
+// (dgRMatrix@j, 4 bytes each) are larger than the row as a bitmap over the cells (n_cells / 8 bytes: 1.25 bytes per
+// id at 10 %).  hs_api.cu packs such rows on the host while earlier buffers are on the link; this kernel restores the
+// ids: row r of the piece owns words [r * words, (r + 1) * words) and the ids go to cols[ptr[r] ...), ascending.
+// One CTA per row: popcount per 64-bit word, block scan, every thread expands its word.
+__global__ void __launch_bounds__(256)
+k_bitmap_to_ids(const unsigned long long* __restrict__ bits, int64_t words, const int64_t* __restrict__ ptr,
+                int32_t* __restrict__ cols, int* __restrict__ flags) {
+  __shared__ unsigned int wsum[8];
+  __shared__ unsigned int carry;
+  const int row = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = ptr[row];
+  const unsigned int nnz = (unsigned int)(ptr[row + 1] - b);
+  const unsigned long long* w = bits + (int64_t)row * words;
+  if (threadIdx.x == 0) carry = 0u;
+  __syncthreads();
+  for (int64_t w0 = 0; w0 < words; w0 += 256) {
+    const int64_t wi = w0 + threadIdx.x;
+    unsigned long long x = wi < words ? __ldg(w + wi) : 0ull;
+    const unsigned int c = (unsigned int)__popcll(x);
+    unsigned int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    unsigned int before = carry;
+    for (int k = 0; k < warp; ++k) before += wsum[k];
+    unsigned int at = before + incl - c;
+    const int32_t id0 = (int32_t)(wi * 64);
+    while (x) {
+      const int bit = __ffsll((long long)x) - 1;
+      x &= x - 1;
+      if (at < nnz) cols[b + at] = id0 + bit;
+      ++at;
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) carry = before + incl;
+    __syncthreads();
+  }
+  if (flags && threadIdx.x == 0 && carry != nnz) atomicOr(flags, 1);      // a bitmap that does not match its row length
+}
+
 }  // namespace
 
 // cp: column pointers (int32 or int64, n_cols + 1), ri: 0-based row ids (ascending inside a column, distinct),
@@ -140,4 +186,13 @@ int hs_run_csc_to_csr_f32(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, con
 int hs_run_csc_to_csr_f64(hs_ctx* ctx, const int64_t* cp, const int32_t* ri, const double* x, int64_t n_rows, int64_t n_cols,
                           int64_t nnz, int64_t* p_out, int32_t* j_out, double* x_out) {
   return convert_impl<int64_t, double, double>(ctx, cp, ri, x, n_rows, n_cols, nnz, p_out, j_out, x_out);
+}
+
+// ids of `n_rows` rows from their bitmaps (see k_bitmap_to_ids); ptr_dev: the rows' pointers into cols_dev
+int hs_run_bitmap_to_ids(hs_ctx* ctx, const void* bits_dev, int64_t words, const int64_t* ptr_dev, int64_t n_rows,
+                         int32_t* cols_dev, int* flags_dev, cudaStream_t st) {
+  if (n_rows <= 0) return HS_OK;
+  k_bitmap_to_ids<<<(unsigned)n_rows, 256, 0, st>>>((const unsigned long long*)bits_dev, words, ptr_dev, cols_dev, flags_dev);
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
 }

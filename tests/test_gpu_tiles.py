@@ -148,3 +148,41 @@ def test_randomization_batch_through_tiles(ctx):
     mask = np.ones_like(got_b, bool)
     mask[1, 3] = False
     _check(got_b[mask], want[mask])
+
+
+def test_packed_id_upload_is_transparent(ctx, monkeypatch):
+    """Rows with more than ~4 % stored values cross PCIe as bitmaps over the cells and are expanded on the device
+    (hs_api.cu: pack_ids, hs_convert.cu: k_bitmap_to_ids).  Same ids on the device, so the scores are bit-identical to
+    the plain upload -- over several pieces of rows, several ring buffers per piece, pinned or pageable, and when one
+    piece holds an unsorted row (that piece then goes up as it is)."""
+    n, m = 3001, 6000
+    x, labels = synth.make_embedding(n, 4, seed=21)
+    xs, _, _ = ho.scale_coords(x)
+    grid = synth.make_grid(xs, 40, seed=21)
+    p, j, v = synth.make_csr_numpy(m, n, 0.10, labels, seed=21)
+    ctx.density(xs, grid)
+    monkeypatch.setenv("HS_PACK_IDS", "0")
+    plain = ctx.dkl_csr(p, j, v)
+    monkeypatch.setenv("HS_PACK_IDS", "1")
+    monkeypatch.setenv("HS_PIECE_ROWS", "700")
+    monkeypatch.setenv("HS_PIECE_VALUES", "200000")
+    monkeypatch.setenv("HS_STAGE_VALUES", "30000")       # a ring buffer holds ~300 rows' bitmaps
+    packed = ctx.dkl_csr(p, j, v)
+    np.testing.assert_array_equal(plain, packed)
+    # the oracle on a few rows, for good measure
+    ref = ho.density_stage(xs, grid)
+    rows = [0, 699, 700, 5999]
+    sub = ho.RowSparse(p=np.concatenate([[0], np.cumsum([p[r + 1] - p[r] for r in rows])]).astype(np.int64),
+                       j=np.concatenate([j[p[r]:p[r + 1]] for r in rows]), x=np.concatenate([v[p[r]:p[r + 1]] for r in rows]),
+                       shape=(len(rows), n))
+    _check(packed[rows], ho.dkl_observed(sub, ref["density"], ref["Q"]))
+    # an unsorted row in the third piece
+    j2, v2 = j.copy(), v.copy()
+    a, b = int(p[1500]), int(p[1501])
+    j2[a], j2[b - 1] = j2[b - 1], j2[a]
+    v2[a], v2[b - 1] = v2[b - 1], v2[a]
+    swapped = ctx.dkl_csr(p, j2, v2)
+    ok = np.ones(m, bool)
+    ok[1500] = False
+    np.testing.assert_array_equal(swapped[ok], plain[ok])
+    assert abs(swapped[1500] - plain[1500]) <= 2e-5 * abs(plain[1500])      # scored by the gather kernel
