@@ -75,6 +75,8 @@ struct hs_ctx {
   DevBuf umma_flags;
   DevBuf prof_x, prof_out;     // hs_profile_*: uploaded fp64 values, gene x grid result
   DevBuf tile_ent, tile_ws;    // tile path of the sparse contraction: tile-major entries, cuts / region / tile tables
+  DevBuf dbg_times;            // HS_TILE_DEBUG: per-CTA timestamps
+  DevBuf zeros;                // a block of zeros (hs_tiles.cu: operand tiles are cleared by bulk copies of it)
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, (id, value) pairs, values of the selected rows
   DevBuf conv_cp, conv_ri, conv_x, conv_p, conv_j, conv_xo;   // hs_csc_to_csr (host form): inputs and outputs

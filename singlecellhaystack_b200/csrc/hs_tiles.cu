@@ -36,6 +36,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <vector>
+
 #include "hs_common.cuh"
 #include "hs_prp.cuh"
 #include "hs_ptx.cuh"
@@ -353,6 +355,8 @@ struct TileMmaParams {
   int out_n_perm;                         // > 0: row = s * n_perm + r is written to out[s + r * n_sel]
   int64_t out_n_sel;
   const int* flags;                       // bit 0 set by the bucketing: the fallback kernel owns the output
+  const unsigned char* zeros;             // kATileBytes of zeros (the copy engine clears the operand tiles with it)
+  unsigned long long* dbg_times;          // development aid: [CTA][2] start / end of every CTA (globaltimer, ns)
   long long* dbg;                         // optional (HS_TILE_DEBUG): cycles the roles of one CTA spend waiting
   int dbg_block;                          // the CTA that reports (HS_TILE_DEBUG=<tile row>; default: mid-grid)
 };
@@ -731,7 +735,7 @@ constexpr int kS1 = 3;                                   // operand stages = acc
 // 13 chunks of 512 entries per stage made the densest tile rows loader-bound at 7300 clk per stage)
 constexpr int kRing1Slots = 4, kRing1Entries = 1024, kRing1SlotBytes = kRing1Entries * 8;
 constexpr int kProducers1 = 4;                           // A-producer warps (the scatter runs at ~0.5 entries/clk per warp)
-constexpr int kMma1Threads = 32 * (10 + kProducers1);    // warps 0-7 epilogue, 8 loader, 9.. producers, last: MMA issuer
+constexpr int kMma1Threads = 32 * (11 + kProducers1);    // warps 0-7 epilogue, 8 loader, 9.. producers, then the MMA issuer and the stager
 constexpr size_t kSmem1Stage = (size_t)kATileBytes + kBStageBytes;          // 64 KB: A_hi, A_lo, D_hi, D_lo
 constexpr size_t kSmem1 = 1024 + kS1 * kSmem1Stage + kRing1Slots * kRing1SlotBytes + 512;
 
@@ -752,16 +756,18 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
   auto acc_full = [&](int b) { return bar_base + 8u * (9 + b); };                // 9..11  (commit)
   auto acc_empty = [&](int b) { return bar_base + 8u * (12 + b); };              // 12..14 (8 epilogue warps)
   auto ring_full = [&](int sl) { return bar_base + 8u * (15 + sl); };                    // 15..22 (tx)
-  auto ring_empty = [&](int sl) { return bar_base + 8u * (15 + kRing1Slots + sl); };     // 23..30 (the producer warps)
+  auto ring_empty = [&](int sl) { return bar_base + 8u * (15 + kRing1Slots + sl); };     // 19..22 (the producer warps)
+  auto zero_full = [&](int st) { return bar_base + 8u * (15 + 2 * kRing1Slots + st); };   // 23..25 (tx): the A tiles are zeroed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tr = blockIdx.x % p.n_tr, seg = blockIdx.x / p.n_tr;
   const int s0 = seg * p.slabs_per_seg;
   const int n_st = hs_max(0, hs_min(p.n_slabs, s0 + p.slabs_per_seg) - s0);
-  constexpr int kLoader = 8, kProd0 = 9, kIssuer = 9 + kProducers1;
+  constexpr int kLoader = 8, kProd0 = 9, kIssuer = 9 + kProducers1, kStager = 10 + kProducers1;
   // development aid (HS_TILE_DEBUG): cycles the non-epilogue roles of one mid-grid CTA spend blocked on each barrier
   const bool dbg_on = p.dbg != nullptr && (int)blockIdx.x == p.dbg_block && warp >= 8;
   long long w_acc[3] = {0, 0, 0};
+  long long t_zero = 0, t_scatter = 0, t_fence = 0;
   auto twait = [&](uint32_t bar, uint32_t parity, int slot) {
     if (dbg_on) {
       const long long t0 = clock64();
@@ -772,6 +778,11 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
     }
   };
   const long long t_begin = clock64();
+  if (p.dbg_times && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg_times[2 * blockIdx.x] = t;
+  }
 
   if (threadIdx.x == 0) {
     for (int st = 0; st < kS1; ++st) {
@@ -780,6 +791,7 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
       mbar_init(stage_empty(st), 1);
       mbar_init(acc_full(st), 1);
       mbar_init(acc_empty(st), 8);
+      mbar_init(zero_full(st), 1);
     }
     for (int sl = 0; sl < kRing1Slots; ++sl) {
       mbar_init(ring_full(sl), 1);
@@ -875,15 +887,16 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
         umma_commit(stage_empty(st));
       }
     }
-  } else if (warp >= kProd0) {
-    // ================= A producers: each zero-fills its share of the tile, then they take the entry chunks in turn ======
-    const int pw = warp - kProd0;
-    uint32_t seq = 0;
-    for (int i = 0; i < n_st; ++i) {
-      const int st = i % kS1;
-      const uint32_t use = (uint32_t)(i / kS1);
-      if (i >= kS1) twait(stage_empty(st), (use - 1) & 1, 0);
-      if (pw == 0 && lane == 0) {
+  } else if (warp == kStager) {
+    // ================= stager: as soon as the MMAs release a stage, its A tiles are zeroed and its density tiles fetched,
+    //                   both by the copy engine (a 32 KB block of zeros sits in L2) =================
+    if (lane == 0) {
+      for (int i = 0; i < n_st; ++i) {
+        const int st = i % kS1;
+        const uint32_t use = (uint32_t)(i / kS1);
+        if (i >= kS1) twait(stage_empty(st), (use - 1) & 1, 0);
+        mbar_arrive_expect_tx(zero_full(st), kATileBytes);
+        bulk_g2s(a_addr(st), p.zeros, kATileBytes, zero_full(st));
         const size_t pf = (size_t)(s0 + i + kBLookahead) * kTileBytes;
         if (i + kBLookahead < n_st) {
           l2_prefetch(p.Dh + pf, kTileBytes);
@@ -894,31 +907,43 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
         bulk_g2s(b_addr(st), p.Dh + off, kTileBytes, b_full(st));
         bulk_g2s(b_addr(st) + kTileBytes, p.Dl + off, kTileBytes, b_full(st));
       }
+    }
+  } else if (warp >= kProd0) {
+    // ================= A producers: every warp scatters its share of every entry chunk into the zeroed tiles ===========
+    const int pw = warp - kProd0;
+    uint32_t seq = 0;
+    for (int i = 0; i < n_st; ++i) {
+      const int st = i % kS1;
+      const uint32_t use = (uint32_t)(i / kS1);
+      const long long tp0 = dbg_on ? clock64() : 0;
+      mbar_wait(zero_full(st), use & 1);
       const uint32_t a_hi = a_addr(st), a_lo = a_hi + kTileBytes;
-#pragma unroll 8
-      for (int z = 0; z < kATileBytes / kProducers1 / 512; ++z)
-        sts_zero16(a_hi + (uint32_t)pw * (kATileBytes / kProducers1) + (uint32_t)(z * 512 + lane * 16));
-      asm volatile("bar.sync 1, %0;" ::"n"(32 * kProducers1) : "memory");     // all of it zeroed before any warp scatters
+      const long long tp1 = dbg_on ? clock64() : 0;
+      const long long wait_before = w_acc[1];
       for (;;) {
         const int sl = (int)(seq % kRing1Slots);
         twait(ring_full(sl), (seq / kRing1Slots) & 1, 1);
         const uint32_t meta = ring_meta[sl];
-        if ((seq % kProducers1) == (uint32_t)pw) {
+        {
+          // 32 entries at a time, round robin over the warps; a chunk holds at most eight per lane: all of a lane's loads
+          // are issued before its first store (one shared-memory round trip per chunk instead of one per entry)
           const uint32_t n = meta & 0x7fffffffu;
           const uint32_t rb = ring_base + (uint32_t)sl * kRing1SlotBytes;
-          uint32_t e = lane;
-          for (; e + 96 < n; e += 128) {     // four entries in flight per lane
-            const uint2 e0 = lds_u2(rb + e * 8u), e1 = lds_u2(rb + (e + 32) * 8u);
-            const uint2 e2 = lds_u2(rb + (e + 64) * 8u), e3 = lds_u2(rb + (e + 96) * 8u);
-            sts_u16(a_hi + e0.x, e0.y); sts_u16(a_lo + e0.x, e0.y >> 16);
-            sts_u16(a_hi + e1.x, e1.y); sts_u16(a_lo + e1.x, e1.y >> 16);
-            sts_u16(a_hi + e2.x, e2.y); sts_u16(a_lo + e2.x, e2.y >> 16);
-            sts_u16(a_hi + e3.x, e3.y); sts_u16(a_lo + e3.x, e3.y >> 16);
+          constexpr uint32_t kStep = 32u * kProducers1;
+          constexpr int kPerLane = kRing1Entries / (int)kStep;
+          const uint32_t e0 = (uint32_t)pw * 32u + lane;
+          uint2 ent[kPerLane];
+#pragma unroll
+          for (int u = 0; u < kPerLane; ++u) {
+            const uint32_t e = e0 + (uint32_t)u * kStep;
+            ent[u] = e < n ? lds_u2(rb + e * 8u) : make_uint2(0xffffffffu, 0u);
           }
-          for (; e < n; e += 32) {
-            const uint2 e0 = lds_u2(rb + e * 8u);
-            sts_u16(a_hi + e0.x, e0.y);
-            sts_u16(a_lo + e0.x, e0.y >> 16);
+#pragma unroll
+          for (int u = 0; u < kPerLane; ++u) {
+            if (ent[u].x != 0xffffffffu) {
+              sts_u16(a_hi + ent[u].x, ent[u].y);
+              sts_u16(a_lo + ent[u].x, ent[u].y >> 16);
+            }
           }
         }
         __syncwarp();
@@ -926,9 +951,15 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
         ++seq;
         if (meta >> 31) break;
       }
+      const long long tp2 = dbg_on ? clock64() : 0;
       fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(a_full(st));
+      if (dbg_on) {
+        t_zero += tp1 - tp0;
+        t_scatter += (tp2 - tp1) - (w_acc[1] - wait_before);
+        t_fence += clock64() - tp2;
+      }
     }
   } else if (warp < 8) {
     // ================= epilogue: TMEM -> fp32 registers -> fp64 =================
@@ -998,8 +1029,13 @@ __global__ void __launch_bounds__(kMma1Threads, 1) k_tile_mma1(const TileMmaPara
   if (dbg_on && lane == 0) {
     if (warp == kLoader) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = n_st; p.dbg[2] = w_acc[0]; }
     if (warp == kIssuer) { p.dbg[3] = w_acc[0]; p.dbg[4] = w_acc[1]; p.dbg[5] = w_acc[2]; }
-    if (warp == kProd0) { p.dbg[6] = w_acc[0]; p.dbg[7] = w_acc[1]; }
+    if (warp == kProd0) { p.dbg[6] = w_acc[0]; p.dbg[7] = w_acc[1]; p.dbg[10] = t_zero; p.dbg[11] = t_scatter; p.dbg[12] = t_fence; }
     if (warp == kProd0 + 1) { p.dbg[8] = w_acc[0]; p.dbg[9] = w_acc[1]; }
+  }
+  if (p.dbg_times && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg_times[2 * blockIdx.x + 1] = t;
   }
   // ---- teardown; the last CTA of this tile row runs the KL epilogue ----
   tc_fence_before();
@@ -1180,11 +1216,32 @@ static int launch_tile_mma(hs_ctx* ctx, const uint2* entries, const unsigned lon
   int form = 1;      // 1: one tile row per CTA, three stages (k_tile_mma1); 2: two tile rows per CTA (k_tile_mma)
   if (const char* e = getenv("HS_TILE_FORM")) form = atoi(e) == 2 ? 2 : 1;
   const int n_units = form == 1 ? n_tr : n_pairs;
+  // ... and among the segment counts around that, the one whose CTAs come out closest to whole waves (79 tile rows
+  // x 15 segments is one CTA more than eight waves of 148: a ninth wave for a single CTA)
   int64_t want_seg = ((int64_t)ctx->sm_count * 8 + n_units - 1) / n_units;
-  if (const char* e = getenv("HS_TILE_SEGMENTS")) want_seg = hs_max(1, atoi(e));
-  int n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(want_seg, n_slabs / 64));
-  int slabs_per_seg = (n_slabs + n_seg - 1) / n_seg;
-  slabs_per_seg = (slabs_per_seg + kFlushStages - 1) / kFlushStages * kFlushStages;
+  const int64_t max_seg = hs_max<int64_t>(1, n_slabs / 64);
+  auto seg_len = [&](int64_t sg) {
+    const int64_t per = (n_slabs + sg - 1) / sg;
+    return (per + kFlushStages - 1) / kFlushStages * kFlushStages;
+  };
+  if (const char* e = getenv("HS_TILE_SEGMENTS")) {
+    want_seg = hs_max(1, atoi(e));
+  } else {
+    int64_t best = hs_min<int64_t>(want_seg, max_seg), best_cost = -1;
+    for (int64_t sg = hs_max<int64_t>(1, want_seg / 2); sg <= hs_min<int64_t>(max_seg, want_seg * 2); ++sg) {
+      const int64_t len = seg_len(sg);
+      const int64_t segs = (n_slabs + len - 1) / len;
+      const int64_t waves = (segs * n_units + ctx->sm_count - 1) / ctx->sm_count;
+      const int64_t cost = waves * (len + 24);          // + a CTA's fixed cost, in stages
+      if (best_cost < 0 || cost < best_cost || (cost == best_cost && sg > best)) {
+        best = sg;
+        best_cost = cost;
+      }
+    }
+    want_seg = best;
+  }
+  int n_seg = (int)hs_max<int64_t>(1, hs_min<int64_t>(want_seg, max_seg));
+  int slabs_per_seg = (int)seg_len(n_seg);
   n_seg = (n_slabs + slabs_per_seg - 1) / slabs_per_seg;
   const int ldP = npad;
   const int64_t seg_stride = (int64_t)n_pairs * 2 * kTM * ldP;
@@ -1215,11 +1272,19 @@ static int launch_tile_mma(hs_ctx* ctx, const uint2* entries, const unsigned lon
   prm.out_n_perm = out_n_perm;
   prm.out_n_sel = out_n_sel;
   prm.flags = flags;
+  HS_TRY(hs_ensure(ctx, ctx->zeros, kATileBytes));
+  HS_CUDA(ctx, cudaMemsetAsync(ctx->zeros.p, 0, kATileBytes, st));
+  prm.zeros = (const unsigned char*)ctx->zeros.p;
   prm.dbg = nullptr;
+  prm.dbg_times = nullptr;
   if (dbg) {
     HS_TRY(hs_ensure(ctx, ctx->umma_flags, 256));
     HS_CUDA(ctx, cudaMemsetAsync(ctx->umma_flags.p, 0, 256, st));
     prm.dbg = (long long*)((char*)ctx->umma_flags.p + 64);
+    if (form == 1) {
+      HS_TRY(hs_ensure(ctx, ctx->dbg_times, sizeof(unsigned long long) * 2 * (size_t)n_tr * (size_t)n_seg));
+      prm.dbg_times = (unsigned long long*)ctx->dbg_times.p;
+    }
   }
   {
     const int units = form == 1 ? n_tr : n_pairs;
@@ -1244,12 +1309,33 @@ static int launch_tile_mma(hs_ctx* ctx, const uint2* entries, const unsigned lon
     cudaEventElapsedTime(&t_mma, ev[2], ev[3]);
     for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
     fprintf(stderr, "[tile dbg] prepare %.3f ms, fill / generate %.3f ms, mma %.3f ms\n", t_cut, t_fill, t_mma);
+    if (prm.dbg_times) {
+      const size_t n_cta = (size_t)n_tr * n_seg;
+      std::vector<unsigned long long> t(2 * n_cta);
+      cudaMemcpy(t.data(), prm.dbg_times, sizeof(unsigned long long) * t.size(), cudaMemcpyDeviceToHost);
+      unsigned long long t0 = ~0ull, t1 = 0, dmin = ~0ull, dmax = 0;
+      double dsum = 0;
+      for (size_t c = 0; c < n_cta; ++c) {
+        t0 = hs_min(t0, t[2 * c]);
+        t1 = hs_max(t1, t[2 * c + 1]);
+        const unsigned long long d = t[2 * c + 1] - t[2 * c];
+        dmin = hs_min(dmin, d);
+        dmax = hs_max(dmax, d);
+        dsum += (double)d;
+      }
+      // first / last tile row of the middle segment, and the same tile row in the first and last segments
+      auto dur = [&](int tr, int sg) { return (double)(t[2 * ((size_t)sg * n_tr + tr) + 1] - t[2 * ((size_t)sg * n_tr + tr)]) * 1e-3; };
+      fprintf(stderr, "[tile dbg] %zu CTAs: span %.3f ms, CTA time min %.1f mean %.1f max %.1f us, busy SM share %.2f | tile row 0 / mid / last "
+                      "in the middle segment: %.1f %.1f %.1f us | stages per CTA %d\n",
+              n_cta, (double)(t1 - t0) * 1e-6, (double)dmin * 1e-3, dsum / (double)n_cta * 1e-3, (double)dmax * 1e-3,
+              dsum / ((double)(t1 - t0) * ctx->sm_count), dur(0, n_seg / 2), dur(n_tr / 2, n_seg / 2), dur(n_tr - 1, n_seg / 2), slabs_per_seg);
+    }
     cudaMemcpy(h, prm.dbg, sizeof(h), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tile dbg] rows %lld pairs %d seg %d | CTA: %lld clk over %lld stages (%.0f/stage) | loader wait ring_empty %lld | "
                     "mma wait acc_empty %lld a_full %lld b_full %lld | producer0 wait stage_empty %lld ring_full %lld | "
-                    "producer1 wait stage_empty %lld ring_full %lld\n",
+                    "producer1 wait stage_empty %lld ring_full %lld | producer0 zero+sync %lld scatter %lld fence %lld\n",
             (long long)n_rows, n_pairs, n_seg, h[0], h[1], h[1] ? (double)h[0] / (double)h[1] : 0.0, h[2], h[3], h[4], h[5], h[6], h[7],
-            h[8], h[9]);
+            h[8], h[9], h[10], h[11], h[12]);
   }
   return HS_OK;
 }
