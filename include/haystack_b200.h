@@ -159,6 +159,14 @@ int hs_dkl_perm_csr_seeded(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, 
  * n_cells x n_perm index matrix.  hs_perm_sample(seed, stream_base + r, n_cells, n_cells, ...) returns pi_r. */
 int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t seed, uint64_t stream_base,
                              double* out);
+
+/* The dense randomization of ALL selected genes in one call (the whole loop R/haystack_continuous.R:250-265): row
+ * sel_rows[s] (0-based) of the n_genes x n_cells column-major matrix `expr` (leading dimension ld), n_perm seeded
+ * randomizations each, stream of (s, r) = stream_base + s * n_perm + r -- the same draws as n_sel calls of
+ * hs_dkl_perm_dense_seeded.  Nothing but the selected rows crosses the link; uploads overlap the scoring; one wait.
+ * out: n_sel x n_perm column-major (all.D_KL.randomized). */
+int hs_dkl_perm_dense_seeded_batch(hs_ctx* ctx, const double* expr, int64_t ld, const int64_t* sel_rows,
+                                   int64_t n_sel, int n_perm, uint64_t seed, uint64_t stream_base, double* out);
 /* hs_dkl_csr and hs_dkl_perm_csr_seeded for the rows sel_rows[0..n_sel) (0-based row numbers of the same
  * matrix, in the order of genes.to.randomize) in one call: the randomization batch is launched first and
  * computes while the matrix is still being uploaded.  Results are bit-identical to the two separate calls
@@ -225,6 +233,13 @@ int hs_row_stats_csr(hs_ctx* ctx, const void* p, int p_is_64, const double* x, i
  * relative differences of order 1e-8 from the above). */
 int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_genes,
                          int64_t n_cells, double* mean_dev, double* sd_dev);
+
+/* Gene selection on the device (R/haystack_continuous.R:222, :227-236): coeffVar = (sd + 1e-300) / (mean + 1e-300)
+ * of device-resident row statistics (hs_row_stats_csr_dev), order(coeffVar) -- stable, NaN last -- and the rows at
+ * `ranks` (0-based positions in that order; the positions themselves are the reference's integer arithmetic on seq()
+ * and stay with the caller).  cv_dev_out: device fp64[n_genes] or NULL; rows_out: host int64[n_ranks], 0-based. */
+int hs_select_by_cv_dev(hs_ctx* ctx, const double* mean_dev, const double* sd_dev, int64_t n_genes,
+                        const int64_t* ranks, int64_t n_ranks, double* cv_dev_out, int64_t* rows_out);
 
 /* ---- CSC -> CSR (the step before the sparse path; optional) -------------------------------- */
 /* as(expression, "RsparseMatrix") (R/haystack_continuous.R:113-116) on the device: a stable counting sort by

@@ -39,6 +39,7 @@ SIGNATURES = {
     "hs_dkl_perm_csr": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
     "hs_dkl_perm_csr_seeded": (_int, [_vp, _vp, _i64, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
     "hs_dkl_perm_dense_seeded": (_int, [_vp, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
+    "hs_dkl_perm_dense_seeded_batch": (_int, [_vp, _vp, _i64, _vp, _i64, _int, C.c_uint64, C.c_uint64, _vp]),
     "hs_dkl_perm_dense_seeded_dev": (_int, [_vp, _vp, _int, C.c_uint64, C.c_uint64, _vp]),
     "hs_dkl_csr_randomized": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp, _i64, _int, C.c_uint64, C.c_uint64, _vp, _vp]),
     "hs_perm_sample": (_int, [C.c_uint64, C.c_uint64, _i64, _i64, _int, _vp]),
@@ -58,6 +59,7 @@ SIGNATURES = {
     "hs_profile_dense": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_row_stats_csr": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _vp, _vp]),
     "hs_row_stats_csr_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "hs_select_by_cv_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "hs_csc_to_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hs_csc_to_csr_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hs_r_rng_create": (_int, [C.c_uint32, _int, C.POINTER(_vp)]),

@@ -1353,6 +1353,76 @@ int hs_dkl_perm_dense_seeded(hs_ctx* ctx, const double* v, int n_perm, uint64_t 
   } HS_ABI_CATCH(ctx)
 }
 
+// The dense randomization of ALL selected genes in one call (R/haystack_continuous.R:250-265, the whole loop over
+// genes.to.randomize): row sel_rows[s] of the column-major expression matrix, n_perm seeded randomizations each,
+// streams stream_base + s * n_perm + r as in the sparse form.  No ids cross the link (the reference's loop would
+// need an n_cells x n_perm index matrix per gene); the rows are gathered by the host threads, two staging buffers
+// keep the upload of gene s + 1 under the scoring of gene s, and the caller waits once.  out: n_sel x n_perm
+// column-major, like all.D_KL.randomized.
+int hs_dkl_perm_dense_seeded_batch(hs_ctx* ctx, const double* expr, int64_t ld, const int64_t* sel_rows, int64_t n_sel,
+                                   int n_perm, uint64_t seed, uint64_t stream_base, double* out) {
+  try {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (!expr || !out || !sel_rows || n_sel < 0 || n_perm <= 0 || ld <= 0)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense_seeded_batch: bad arguments");
+  for (int64_t s = 0; s < n_sel; ++s)
+    if (sel_rows[s] < 0 || sel_rows[s] >= ld)
+      return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_dense_seeded_batch: selected row out of range");
+  if (n_sel == 0) return HS_OK;
+  const int64_t N = ctx->N;
+  HS_TRY(ensure_ring(ctx, sizeof(float) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->stage_x[0], sizeof(float) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->stage_x[1], sizeof(float) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->out_rand, sizeof(double) * (size_t)(n_sel * n_perm)));
+  cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+  HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[0], st));
+  HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[0], 0));
+  ScopedTimer tm(ctx, HS_T_PERM);
+  int ring_k = 0;
+  for (int64_t s = 0; s < n_sel; ++s) {
+    const int b = (int)(s & 1);
+    // gather the strided row as fp32 into a pinned buffer (host threads), then one contiguous copy
+    const int k = ring_k;
+    ring_k = (ring_k + 1) % hs_ctx::kRing;
+    if (ctx->ring_busy[k]) {
+      HS_CUDA(ctx, cudaEventSynchronize(ctx->ev_ring[k]));
+      ctx->ring_busy[k] = false;
+    }
+    float* dst = (float*)ctx->ring[k];
+    const double* src = expr + sel_rows[s];
+    auto part = [=](int t, int nt) {
+      const int64_t per = (N + nt - 1) / nt, a = hs_min<int64_t>(N, (int64_t)t * per), e = hs_min<int64_t>(N, a + per);
+      for (int64_t c = a; c < e; ++c) dst[c] = (float)src[c * ld];
+    };
+    if (N < ((int64_t)1 << 16) || host_threads() == 1) {
+      part(0, 1);
+    } else {
+      if (!ctx->pool) ctx->pool = new HostPool(host_threads());
+      const int nt = ctx->pool->size();
+      ctx->pool->run([&](int t) { part(t, nt); });
+    }
+    if (s >= 2) HS_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->ev_done[b], 0));      // gene s - 2 has been scored
+    HS_CUDA(ctx, cudaMemcpyAsync(ctx->stage_x[b].p, dst, sizeof(float) * (size_t)N, cudaMemcpyHostToDevice, cs));
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_ring[k], cs));
+    ctx->ring_busy[k] = true;
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_stage[b], cs));
+    HS_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_stage[b], 0));
+    HS_TRY(hs_run_perm_dense_seeded(ctx, (const float*)ctx->stage_x[b].p, n_perm, seed,
+                                    stream_base + (uint64_t)s * (uint64_t)n_perm,
+                                    (double*)ctx->out_rand.p + s * (int64_t)n_perm));
+    HS_CUDA(ctx, cudaEventRecord(ctx->ev_done[b], st));
+  }
+  tm.stop();
+  std::vector<double> tmp((size_t)(n_sel * n_perm));
+  HS_CUDA(ctx, cudaMemcpyAsync(tmp.data(), ctx->out_rand.p, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int64_t s = 0; s < n_sel; ++s)
+    for (int r = 0; r < n_perm; ++r) out[s + (int64_t)r * n_sel] = tmp[(size_t)(s * n_perm + r)];
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
 int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, int64_t n_genes, int64_t n_cells,
                          double* mean_dev, double* sd_dev) {
   try {
@@ -1361,6 +1431,32 @@ int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, 
   if (n_genes < 0 || n_cells < 1 || !p_dev || !mean_dev || !sd_dev)
     return hs_fail(ctx, HS_ERR_INVALID, "hs_row_stats_csr_dev: bad arguments");
   return hs_run_row_stats_f32(ctx, p_dev, x_dev, n_genes, n_cells, mean_dev, sd_dev);
+  } HS_ABI_CATCH(ctx)
+}
+
+// coeffVar and the rows at the given ranks of order(coeffVar) from device-resident row statistics; see hs_spmm.cu
+int hs_select_by_cv_dev(hs_ctx* ctx, const double* mean_dev, const double* sd_dev, int64_t n_genes, const int64_t* ranks,
+                        int64_t n_ranks, double* cv_dev_out, int64_t* rows_out) {
+  try {
+  HS_TRY(set_device(ctx));
+  if (!mean_dev || !sd_dev || n_genes <= 0 || n_ranks < 0 || (n_ranks > 0 && (!ranks || !rows_out)))
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_select_by_cv_dev: bad arguments");
+  cudaStream_t st = ctx->stream;
+  HS_TRY(hs_ensure(ctx, ctx->out, sizeof(int64_t) * (size_t)(2 * hs_max<int64_t>(n_ranks, 1) + 1)));
+  int64_t* ranks_dev = (int64_t*)ctx->out.p;
+  int64_t* rows_dev = ranks_dev + hs_max<int64_t>(n_ranks, 1);
+  int* flag = (int*)(rows_dev + hs_max<int64_t>(n_ranks, 1));
+  HS_CUDA(ctx, cudaMemsetAsync(flag, 0, sizeof(int), st));
+  if (n_ranks > 0)
+    HS_CUDA(ctx, cudaMemcpyAsync(ranks_dev, ranks, sizeof(int64_t) * (size_t)n_ranks, cudaMemcpyHostToDevice, st));
+  HS_TRY(hs_run_order_by_cv(ctx, mean_dev, sd_dev, n_genes, ranks_dev, n_ranks, cv_dev_out, rows_dev, flag));
+  int h_flag = 0;
+  if (n_ranks > 0)
+    HS_CUDA(ctx, cudaMemcpyAsync(rows_out, rows_dev, sizeof(int64_t) * (size_t)n_ranks, cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaMemcpyAsync(&h_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  HS_CUDA(ctx, cudaStreamSynchronize(st));
+  if (h_flag) return hs_fail(ctx, HS_ERR_INVALID, "hs_select_by_cv_dev: a rank lies outside [0, n_genes)");
+  return HS_OK;
   } HS_ABI_CATCH(ctx)
 }
 

@@ -154,6 +154,8 @@ int hs_run_perm_dense_seeded(hs_ctx* ctx, const float* v_dev, int n_perm, uint64
 int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, int n_perm, uint64_t seed, uint64_t stream_base, double* out_dev,
                        const unsigned long long* unit_stream_dev = nullptr);
+int hs_run_order_by_cv(hs_ctx* ctx, const double* mean_dev, const double* sd_dev, int64_t n, const int64_t* ranks_dev,
+                       int64_t n_ranks, double* cv_dev_out, int64_t* rows_dev_out, int* flag_dev);
 int hs_run_perm_tiles(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total, const float* val_dev,
                       int n_perm, uint64_t seed, uint64_t stream_base, const unsigned long long* unit_stream_dev,
                       const int32_t* sorted_rows_dev, double* out_dev, int* flags);

@@ -1181,3 +1181,60 @@ int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
   return hs_run_slab_spmm(ctx, false, rp, n_rows, 1, nullptr, nullptr, 0, out_dev, n_perm, n_sel,
                           /*allow_tiles=*/false /* ids are only slab-sorted */, nullptr, ctx->perm_cols.p);
 }
+
+// =================================================================================================================
+// Gene selection on the device (R/haystack_continuous.R:222, :227-236): coeffVar = sd / mean of the row statistics
+// (each with the reference's + 1e-300, :82-83), order(coeffVar) -- stable, NaN last, as R's order() and numpy's stable
+// argsort -- and the rows at the requested ranks.  The ranks themselves are the reference's integer arithmetic on
+// seq() and stay with the host (haystack.py: select_genes_to_randomize).
+// =================================================================================================================
+namespace {
+__global__ void k_cv_keys(const double* __restrict__ mean, const double* __restrict__ sd, int64_t n,
+                          double* __restrict__ cv_out, unsigned long long* __restrict__ keys, int32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double cv = (sd[i] + 1e-300) / (mean[i] + 1e-300);
+  if (cv == 0.0) cv = 0.0;                                   // -0 and +0 compare equal in order(): one key
+  if (cv_out) cv_out[i] = cv;
+  unsigned long long b = (unsigned long long)__double_as_longlong(cv);
+  b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);          // ascending unsigned order = ascending double order
+  if (cv != cv) b = ~0ull;                                   // NaN: last, in index order (the sort is stable)
+  keys[i] = b;
+  idx[i] = (int32_t)i;
+}
+__global__ void k_pick_ranks(const int32_t* __restrict__ order, const int64_t* __restrict__ ranks, int64_t n_ranks, int64_t n,
+                             int64_t* __restrict__ rows, int* __restrict__ flags) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_ranks) return;
+  const int64_t r = ranks[k];
+  if (r < 0 || r >= n) {
+    atomicOr(flags, 1);
+    rows[k] = -1;
+    return;
+  }
+  rows[k] = order[r];
+}
+}  // namespace
+
+int hs_run_order_by_cv(hs_ctx* ctx, const double* mean_dev, const double* sd_dev, int64_t n, const int64_t* ranks_dev,
+                       int64_t n_ranks, double* cv_dev_out, int64_t* rows_dev_out, int* flag_dev) {
+  if (n <= 0 || n > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "gene selection: bad number of rows");
+  cudaStream_t st = ctx->stream;
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, (int)n, 0, 64, st);
+  const size_t k_b = ((size_t)n * 8 + 255) & ~(size_t)255, i_b = ((size_t)n * 4 + 255) & ~(size_t)255;
+  HS_TRY(hs_ensure(ctx, ctx->spmm_ws, 2 * k_b + 2 * i_b + ((cub_bytes + 255) & ~(size_t)255)));
+  char* w = (char*)ctx->spmm_ws.p;
+  unsigned long long* keys_in = (unsigned long long*)w;   w += k_b;
+  unsigned long long* keys_out = (unsigned long long*)w;  w += k_b;
+  int32_t* idx_in = (int32_t*)w;                          w += i_b;
+  int32_t* idx_out = (int32_t*)w;                         w += i_b;
+  k_cv_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(mean_dev, sd_dev, n, cv_dev_out, keys_in, idx_in);
+  HS_LAUNCH_CHECK(ctx);
+  HS_CUDA(ctx, cub::DeviceRadixSort::SortPairs(w, cub_bytes, keys_in, keys_out, idx_in, idx_out, (int)n, 0, 64, st));
+  ctx->launches += 3;
+  k_pick_ranks<<<(unsigned)((n_ranks + 255) / 256), 256, 0, st>>>(idx_out, ranks_dev, n_ranks, n, rows_dev_out, flag_dev);
+  HS_LAUNCH_CHECK(ctx);
+  return HS_OK;
+}

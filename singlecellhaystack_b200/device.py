@@ -166,6 +166,24 @@ class DeviceContext:
         self._check(self._lib.hs_row_stats_csr_dev(self._h, _dptr(p_dev), _dptr(x_dev), p_dev.numel() - 1, int(n_cells),
                                                    _dptr(mean_dev), _dptr(sd_dev)), "hs_row_stats_csr_dev")
 
+    def select_by_cv(self, mean, sd, ranks, return_cv=False):
+        """hs_select_by_cv_dev: rows at the 0-based `ranks` of order(coeffVar), coeffVar = (sd + 1e-300) / (mean + 1e-300)
+        (R/haystack_continuous.R:222, :227-236) -- sorted on the device.  mean / sd: the row statistics WITHOUT the
+        1e-300, numpy arrays or device tensors (as hs_row_stats_csr_dev leaves them)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        m = mean if isinstance(mean, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(mean, dtype=np.float64), device=dev)
+        s = sd if isinstance(sd, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(sd, dtype=np.float64), device=dev)
+        if m.dtype != torch.float64 or s.dtype != torch.float64 or m.numel() != s.numel():
+            raise ValueError("mean and sd must be float64 vectors of the same length")
+        r = np.ascontiguousarray(ranks, dtype=np.int64)
+        rows = np.empty(r.size, dtype=np.int64)
+        cv = torch.empty(m.numel(), dtype=torch.float64, device=dev) if return_cv else None
+        torch.cuda.current_stream(dev).synchronize()
+        self._check(self._lib.hs_select_by_cv_dev(self._h, _dptr(m), _dptr(s), int(m.numel()), _ptr(r), int(r.size),
+                                                  _dptr(cv) if cv is not None else None, _ptr(rows)), "hs_select_by_cv_dev")
+        return (rows, cv) if return_cv else rows
+
     # -- K1 -----------------------------------------------------------------------------------
     def density(self, x, grid, w_q=None, want_densities=False, want_nearest=False):
         """hs_density: x (N,d), grid (G,d) in the same (scaled) space.  Returns dict with
@@ -370,6 +388,20 @@ class DeviceContext:
         self._check(self._lib.hs_dkl_perm_dense_seeded(self._h, _ptr(v), int(n_perm), int(seed) % (1 << 64),
                                                        int(stream_base) % (1 << 64), _ptr(out)),
                     "hs_dkl_perm_dense_seeded")
+        return out
+
+    def dkl_perm_dense_seeded_batch(self, expression, rows, n_perm: int, seed: int, stream_base: int = 0) -> np.ndarray:
+        """hs_dkl_perm_dense_seeded_batch: the dense randomization of all `rows` (0-based) of the genes x cells matrix in
+        one call; stream of (s, r) = stream_base + s * n_perm + r.  Returns (len(rows), R)."""
+        e = _f64_colmajor(expression, "expression")
+        if e.ndim != 2 or e.shape[1] != self.shape[0]:
+            raise ValueError("expression must be genes x n_cells")
+        r = np.ascontiguousarray(rows, dtype=np.int64)
+        out = np.empty((r.size, int(n_perm)), dtype=np.float64, order="F")
+        self._check(self._lib.hs_dkl_perm_dense_seeded_batch(self._h, _ptr(e), int(e.shape[0]), _ptr(r), int(r.size),
+                                                             int(n_perm), int(seed) % (1 << 64),
+                                                             int(stream_base) % (1 << 64), _ptr(out)),
+                    "hs_dkl_perm_dense_seeded_batch")
         return out
 
     def dkl_perm_csr(self, vals: list, inds: list, index_base=1) -> np.ndarray:

@@ -99,12 +99,9 @@ def _seq_length_out(frm, to, n):
     return out
 
 
-def select_genes_to_randomize(coeffVar, n_genes_to_randomize, method="heavytails"):
-    """R/haystack_continuous.R:227-236.  Integer arithmetic exactly as R: order() is stable with NA
-    last, as.integer() truncates, floor() floors.  Returns 0-based row indices."""
-    cv = np.asarray(coeffVar, dtype=np.float64)
-    count_genes = cv.size
-    o = np.argsort(cv, kind="stable")
+def selection_ranks(count_genes, n_genes_to_randomize, method="heavytails"):
+    """The 1-based positions in order(coeffVar) that R/haystack_continuous.R:227-236 picks: integer arithmetic exactly
+    as R (as.integer() truncates, floor() floors)."""
     s = int(n_genes_to_randomize)
     if method == "uniform":
         pos = np.floor(_seq_length_out(1, count_genes, s)).astype(np.int64)
@@ -120,6 +117,14 @@ def select_genes_to_randomize(coeffVar, n_genes_to_randomize, method="heavytails
     else:
         # the reference silently leaves genes.to.randomize undefined here and fails later
         raise ValueError("'selection.method.genes.to.randomize' should be either 'uniform' or 'heavytails'")
+    return pos
+
+
+def select_genes_to_randomize(coeffVar, n_genes_to_randomize, method="heavytails"):
+    """R/haystack_continuous.R:227-236: order() is stable with NA last.  Returns 0-based row indices."""
+    cv = np.asarray(coeffVar, dtype=np.float64)
+    pos = selection_ranks(cv.size, n_genes_to_randomize, method)
+    o = np.argsort(cv, kind="stable")
     return o[pos - 1]
 
 
@@ -238,6 +243,7 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         expression = expression.row_subset(~sel_bad) if sparse_in else expression[~sel_bad]
     if gene_names is not None:
         gene_names = [g for g, bad in zip(gene_names, sel_bad) if not bad]
+    stats_raw = (expr_mean[~sel_bad], expr_sd[~sel_bad])      # what hs_select_by_cv_dev takes (it adds the 1e-300 itself)
     expr_mean = expr_mean[~sel_bad] + 1e-300
     expr_sd = expr_sd[~sel_bad] + 1e-300
     _message(verbose, "### Filtered ", int(sel_bad.sum()), " genes with zero variance...")
@@ -317,8 +323,13 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         # The gene selection (:222-236) needs only the row statistics, so it can precede the scoring; that lets
         # the sparse path with device draws score the genes and the randomization batch in one call.
         coeffVar = expr_sd / expr_mean                                                   # :222
-        genes_to_randomize = select_genes_to_randomize(coeffVar, n_genes_to_randomize,
-                                                       selection_method_genes_to_randomize)
+        if isinstance(row_stats, str):
+            # statistics from the device: the order(coeffVar) of the selection is taken there as well
+            ranks = selection_ranks(coeffVar.size, n_genes_to_randomize, selection_method_genes_to_randomize)
+            genes_to_randomize = ctx.select_by_cv(stats_raw[0], stats_raw[1], ranks - 1)
+        else:
+            genes_to_randomize = select_genes_to_randomize(coeffVar, n_genes_to_randomize,
+                                                           selection_method_genes_to_randomize)
         info_perm_seed = None
         device_draw = isinstance(perm_source, str)
         if device_draw and perm_source != "device":
@@ -366,9 +377,9 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
             flush()
         elif device_draw:
             perm_seed = int(r_stream.unif_rand() * 2 ** 53) if r_stream is not None else int(rng.integers(0, 2 ** 63))
-            for i, g in enumerate(genes_to_randomize):
-                all_D_KL_randomized[i, :] = ctx.dkl_perm_dense_seeded(expression[int(g)], randomization_count, perm_seed,
-                                                                      stream_base=i * randomization_count)
+            # the whole loop :250-265 in one call: only the selected rows cross the link
+            all_D_KL_randomized[:, :] = ctx.dkl_perm_dense_seeded_batch(expression, genes_to_randomize,
+                                                                        randomization_count, perm_seed)
             info_perm_seed = perm_seed
         else:
             for i, g in enumerate(genes_to_randomize):

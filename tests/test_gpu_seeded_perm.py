@@ -236,3 +236,23 @@ def test_combined_call_equals_separate_calls(ctx, toy):
     from singlecellhaystack_b200.device import HaystackLibraryError
     with pytest.raises(HaystackLibraryError, match="out of range"):
         ctx.dkl_csr_randomized(sp.p, sp.j, sp.x, np.array([500], dtype=np.int64), 5, 1)
+
+
+def test_dense_seeded_batch_equals_single_calls(ctx, toy):
+    """hs_dkl_perm_dense_seeded_batch = the loop R/haystack_continuous.R:250-265 in one call: same streams, same
+    kernels, so bit-identical to n_sel calls of hs_dkl_perm_dense_seeded; and against the oracle fed the same ids."""
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ref = ho.density_stage(xs, toy["grid100"])
+    ctx.density(xs, toy["grid100"])
+    expr = np.asfortranarray(toy["expression"].astype(np.float64))
+    rows = np.array([3, 499, 0, 77, 250])
+    n_perm, seed, base = 9, 1234567, 40
+    got = ctx.dkl_perm_dense_seeded_batch(expr, rows, n_perm, seed, stream_base=base)
+    assert got.shape == (rows.size, n_perm)
+    one = np.stack([ctx.dkl_perm_dense_seeded(expr[r], n_perm, seed, stream_base=base + s * n_perm) for s, r in enumerate(rows)])
+    np.testing.assert_array_equal(got, one)
+    n = expr.shape[1]
+    for s in (0, 4):
+        perms = np.stack([po.prp_sample(seed, base + s * n_perm + r, n, n) for r in range(n_perm)])     # 1-based
+        want = ho.dkl_randomized_dense(expr[[rows[s]]], perms[None], ref["density"], ref["Q"])[0]
+        assert _rel(got[s], want) < RTOL_DKL

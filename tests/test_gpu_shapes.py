@@ -168,3 +168,33 @@ def test_csc_to_csr_device_form_feeds_the_scoring(ctx, toy):
     finally:
         ctx.set_stream(None)
     assert _rel(dkl.cpu().numpy(), toy["dkl100"]) < RTOL
+
+
+def test_gene_selection_on_the_device(ctx):
+    """hs_select_by_cv_dev against the host restatement of R/haystack_continuous.R:222-236: ties (order() is stable),
+    NaN last, negative and zero coefficients, both selection methods, sizes of BASELINE.json's configs."""
+    from singlecellhaystack_b200 import haystack as hk
+    rng = np.random.default_rng(5)
+    for m in (500, 12382, 16811, 30000):
+        mean = rng.gamma(2.0, 1.0, size=m)
+        sd = rng.gamma(2.0, 1.0, size=m)
+        sd[rng.choice(m, m // 10, replace=False)] = sd[0]            # ties in sd ...
+        mean[rng.choice(m, m // 10, replace=False)] = mean[1]        # ... and in mean: tied coefficients
+        dup = rng.choice(m, m // 5, replace=False)
+        mean[dup], sd[dup] = mean[dup[0]], sd[dup[0]]
+        cv = (sd + 1e-300) / (mean + 1e-300)
+        for method in ("heavytails", "uniform"):
+            want = hk.select_genes_to_randomize(cv, 100, method)
+            ranks = hk.selection_ranks(m, 100, method) - 1
+            got, cv_dev = ctx.select_by_cv(mean, sd, ranks, return_cv=True)
+            np.testing.assert_array_equal(got, want)
+            np.testing.assert_array_equal(cv_dev.cpu().numpy(), cv)
+    # the whole order, with NaN, infinities, zeros of both signs and negative coefficients
+    mean = np.array([1.0, 0.0, 2.0, -1.0, np.nan, 1.0, -0.0, 4.0, 1e300, 3.0])
+    sd = np.array([1.0, 1.0, 0.0, 1.0, 1.0, 1.0, 0.0, np.nan, 1.0, 0.0])
+    cv = (sd + 1e-300) / (mean + 1e-300)
+    got = ctx.select_by_cv(mean, sd, np.arange(10))
+    np.testing.assert_array_equal(got, np.argsort(cv, kind="stable"))
+    from singlecellhaystack_b200.device import HaystackLibraryError
+    with pytest.raises(HaystackLibraryError, match="outside"):
+        ctx.select_by_cv(mean, sd, np.array([10]))
