@@ -582,6 +582,9 @@ def run_b200(a):
         dense_extra = run_dense_side(a, ctx, dev, peak)
     if rank == 0 and world == 1 and not a.no_extra_configs and not a.overridden:
         side = run_side_configs(a, ctx, dev)
+    convert_extra = None
+    if rank == 0 and world == 1 and not a.no_dense and a.config == "c5" and not a.overridden:
+        convert_extra = run_convert_side(w, ctx, dev, peak)
 
     # ---- end to end through the host-pointer C ABI (pinned host inputs, H2D inside the timed region) ----
     e2e = None
@@ -623,6 +626,8 @@ def run_b200(a):
             extra["k2_dense_tcgen05"] = dense_extra
         if side:
             extra["configs"] = side
+        if convert_extra is not None:
+            extra["csc_to_csr"] = convert_extra
         extra.update(e2e_extra)
         if extra:
             line["extra"] = extra
@@ -634,6 +639,43 @@ def run_b200(a):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_convert_side(w, ctx, dev, hbm_peak):
+    """as(expression, "RsparseMatrix") on the device (hs_csc_to_csr_dev, R/haystack_continuous.R:113-116) at the full
+    workload: the resident CSR matrix is first transposed into dgCMatrix slots by the same routine (rows = cells), then
+    converted back and compared bit for bit.  Not part of `value`."""
+    import torch
+    m, n, nnz = w.m_local, w.n, w.nnz
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    if free_b < 2.2 * 8 * nnz + (1 << 30):
+        return {"skipped": "not enough free device memory for two more copies of the matrix"}
+    cp = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    ri = torch.empty(nnz, dtype=torch.int32, device=dev)
+    xc = torch.empty(nnz, dtype=torch.float32, device=dev)
+    t = []
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    ctx.csc_to_csr_dev(w.p, w.cols, w.vals, n, m, cp, ri, xc)            # genes x cells CSR == CSC of the transpose
+    ev[1].record()
+    p2 = torch.empty(m + 1, dtype=torch.int64, device=dev)
+    j2 = torch.empty(nnz, dtype=torch.int32, device=dev)
+    x2 = torch.empty(nnz, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize()
+    ev[1].record()
+    ctx.csc_to_csr_dev(cp, ri, xc, m, n, p2, j2, x2)
+    ev[2].record()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(p2, w.p) and torch.equal(j2, w.cols) and torch.equal(x2, w.vals))
+    ms = ev[1].elapsed_time(ev[2])
+    del cp, ri, xc, p2, j2, x2
+    torch.cuda.empty_cache()
+    alg = 2.0 * 8.0 * nnz                                                   # read ids + values, write ids + values
+    return {"rows": m, "cols": n, "nnz": nnz, "ms": ms, "round_trip_bit_identical": same,
+            "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg},
+            "note": "dgCMatrix slots -> dgRMatrix slots (ids + fp32 values), host synchronisation of the call included"}
 
 
 def run_dense_side(a, ctx, dev, hbm_peak):

@@ -245,7 +245,8 @@ int hs_select_by_cv_dev(hs_ctx* ctx, const double* mean_dev, const double* sd_de
 /* as(expression, "RsparseMatrix") (R/haystack_continuous.R:113-116) on the device: a stable counting sort by
  * row id, column ids ascending inside every row, bit-reproducible.  cp: column pointers of the dgCMatrix
  * (@p, int32 or int64, n_cols + 1 entries), ri: @i (0-based row ids), x: @x.  Outputs: the dgRMatrix slots
- * p_out int64[n_rows + 1], j_out int32[nnz], x_out double[nnz].  At most 57344 rows per call. */
+ * p_out int64[n_rows + 1], j_out int32[nnz], x_out double[nnz].  Any number of rows (bands of 56 000 rows, one pass
+ * over the entries per band). */
 int hs_csc_to_csr(hs_ctx* ctx, const void* cp, int cp_is_64, const int32_t* ri, const double* x,
                   int64_t n_rows, int64_t n_cols, int64_t* p_out, int32_t* j_out, double* x_out);
 /* Device-resident form (int64 column pointers, fp32 values), producing what hs_dkl_csr_dev consumes. */

@@ -10,7 +10,8 @@
 //                      distinct rows, so the threads of the CTA take them in parallel and bump the row's
 //                      cursor with a plain read-modify-write.  Column ids therefore come out ascending in
 //                      every row (what the slab kernel and R's dgRMatrix both want), bit-reproducibly.
-// Row counters live in shared memory (4 bytes per row: up to 56 000 rows per call).
+// Row counters live in shared memory (4 bytes per row): rows are taken in bands of 56 000, one pass over the
+// entries per band -- a single pass for any gene x cell matrix.
 #include <cub/device/device_scan.cuh>
 #include <stdint.h>
 
@@ -22,22 +23,24 @@ constexpr int kConvThreads = 512;
 
 template <typename P>
 __global__ void __launch_bounds__(kConvThreads)
-k_csc_count(const P* __restrict__ cp, const int32_t* __restrict__ ri, int64_t n_rows, int64_t n_cols, int cols_per_block,
-            uint32_t* __restrict__ hist /* [blocks][n_rows] */, int* __restrict__ flags) {
+k_csc_count(const P* __restrict__ cp, const int32_t* __restrict__ ri, int64_t n_rows, int64_t r0, int64_t r1, int64_t n_cols,
+            int cols_per_block, uint32_t* __restrict__ hist /* [blocks][n_rows] */, int* __restrict__ flags) {
+  // rows [r0, r1): the band of rows whose counters fit into shared memory (one launch per band)
   extern __shared__ uint32_t cnt[];
-  for (int64_t r = threadIdx.x; r < n_rows; r += kConvThreads) cnt[r] = 0;
+  const int64_t nb = r1 - r0;
+  for (int64_t r = threadIdx.x; r < nb; r += kConvThreads) cnt[r] = 0;
   __syncthreads();
   const int64_t c0 = (int64_t)blockIdx.x * cols_per_block, c1 = hs_min<int64_t>(n_cols, c0 + cols_per_block);
   const int64_t e0 = (int64_t)cp[c0], e1 = (int64_t)cp[c1];
   bool bad = false;
   for (int64_t e = e0 + threadIdx.x; e < e1; e += kConvThreads) {
-    const int32_t r = ri[e];
-    if (r < 0 || r >= n_rows) bad = true; else atomicAdd(&cnt[r], 1u);
+    const int64_t r = ri[e];
+    if (r < 0 || r >= n_rows) bad = true; else if (r >= r0 && r < r1) atomicAdd(&cnt[r - r0], 1u);
   }
   if (bad) atomicOr(flags, 1);
   __syncthreads();
-  uint32_t* out = hist + (int64_t)blockIdx.x * n_rows;
-  for (int64_t r = threadIdx.x; r < n_rows; r += kConvThreads) out[r] = cnt[r];
+  uint32_t* out = hist + (int64_t)blockIdx.x * n_rows + r0;
+  for (int64_t r = threadIdx.x; r < nb; r += kConvThreads) out[r] = cnt[r];
   // (a block past the last column cannot exist: n_blocks is derived from cols_per_block)
 }
 
@@ -62,20 +65,21 @@ k_csc_offsets(uint32_t* __restrict__ hist, int n_blocks, int64_t n_rows, int64_t
 template <typename P, typename TI, typename TO>
 __global__ void __launch_bounds__(kConvThreads)
 k_csc_scatter(const P* __restrict__ cp, const int32_t* __restrict__ ri, const TI* __restrict__ x, int64_t n_rows,
-              int64_t n_cols, int cols_per_block, const uint32_t* __restrict__ hist, const int64_t* __restrict__ p_out,
-              int32_t* __restrict__ j_out, TO* __restrict__ x_out) {
-  extern __shared__ uint32_t pos[];   // cursor of every row inside the row, for this block
-  const uint32_t* mine = hist + (int64_t)blockIdx.x * n_rows;
-  for (int64_t r = threadIdx.x; r < n_rows; r += kConvThreads) pos[r] = mine[r];
+              int64_t r0, int64_t r1, int64_t n_cols, int cols_per_block, const uint32_t* __restrict__ hist,
+              const int64_t* __restrict__ p_out, int32_t* __restrict__ j_out, TO* __restrict__ x_out) {
+  extern __shared__ uint32_t pos[];   // cursor of every row of the band inside the row, for this block
+  const uint32_t* mine = hist + (int64_t)blockIdx.x * n_rows + r0;
+  const int64_t nb = r1 - r0;
+  for (int64_t r = threadIdx.x; r < nb; r += kConvThreads) pos[r] = mine[r];
   __syncthreads();
   const int64_t c0 = (int64_t)blockIdx.x * cols_per_block, c1 = hs_min<int64_t>(n_cols, c0 + cols_per_block);
   for (int64_t c = c0; c < c1; ++c) {
     const int64_t e0 = (int64_t)cp[c], e1 = (int64_t)cp[c + 1];
     for (int64_t e = e0 + threadIdx.x; e < e1; e += kConvThreads) {
-      const int32_t r = ri[e];
-      if (r < 0 || r >= n_rows) continue;            // flagged by the counting pass
-      const uint32_t k = pos[r];                     // rows are distinct inside a column: no race
-      pos[r] = k + 1;
+      const int64_t r = ri[e];
+      if (r < r0 || r >= r1) continue;               // another band's row (ids outside [0, n_rows): flagged by the counting pass)
+      const uint32_t k = pos[r - r0];                // rows are distinct inside a column: no race
+      pos[r - r0] = k + 1;
       const int64_t o = p_out[r] + k;
       j_out[o] = (int32_t)c;
       x_out[o] = (TO)x[e];
@@ -138,14 +142,18 @@ template <typename P, typename TI, typename TO>
 static int convert_impl(hs_ctx* ctx, const P* cp, const int32_t* ri, const TI* x, int64_t n_rows, int64_t n_cols,
                         int64_t nnz, int64_t* p_out, int32_t* j_out, TO* x_out) {
   cudaStream_t st = ctx->stream;
-  const size_t smem = sizeof(uint32_t) * (size_t)hs_max<int64_t>(n_rows, 1);
-  if (smem > 224 * 1024)
-    return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: %lld rows exceed the 57344 a call can take (convert row blocks "
-                   "separately or on the host)", (long long)n_rows);
-  // column blocks: enough CTAs to fill the machine several times over, at most 1024 histograms
-  int n_blocks = (int)hs_min<int64_t>(hs_max<int64_t>(n_cols, 1), hs_min<int64_t>(1024, (int64_t)ctx->sm_count * 8));
+  // row counters live in shared memory: bands of 56 000 rows, one pass over the entries per band (a gene x cell matrix
+  // has fewer genes than that; its transpose needs a band per 56 000 cells)
+  const int64_t band = 56000;
+  const int64_t n_bands = (hs_max<int64_t>(n_rows, 1) + band - 1) / band;
+  const size_t smem = sizeof(uint32_t) * (size_t)hs_min<int64_t>(hs_max<int64_t>(n_rows, 1), band);
+  // column blocks: enough CTAs to fill the machine several times over, at most 1024 histograms and 2 GB of them
+  int64_t max_blocks = hs_min<int64_t>(1024, (int64_t)ctx->sm_count * 8);
+  max_blocks = hs_max<int64_t>(1, hs_min<int64_t>(max_blocks, ((int64_t)2 << 30) / (4 * hs_max<int64_t>(n_rows, 1))));
+  int n_blocks = (int)hs_min<int64_t>(hs_max<int64_t>(n_cols, 1), max_blocks);
   const int cols_per_block = (int)((hs_max<int64_t>(n_cols, 1) + n_blocks - 1) / n_blocks);
   n_blocks = (int)((hs_max<int64_t>(n_cols, 1) + cols_per_block - 1) / cols_per_block);
+  if (n_rows + 1 > 0x7fffffffLL) return hs_fail(ctx, HS_ERR_INVALID, "hs_csc_to_csr: too many rows");
   size_t scan_ws = 0;
   HS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, scan_ws, (const int64_t*)nullptr, (int64_t*)nullptr, (int)(n_rows + 1), st));
   auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
@@ -160,16 +168,22 @@ static int convert_impl(hs_ctx* ctx, const P* cp, const int32_t* ri, const TI* x
   HS_CUDA(ctx, cudaMemsetAsync(flags, 0, 256, st));
   HS_CUDA(ctx, cudaFuncSetAttribute(k_csc_count<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   HS_CUDA(ctx, cudaFuncSetAttribute(k_csc_scatter<P, TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_csc_count<P><<<n_blocks, kConvThreads, smem, st>>>(cp, ri, n_rows, n_cols, cols_per_block, hist, flags);
-  HS_LAUNCH_CHECK(ctx);
+  for (int64_t b = 0; b < n_bands; ++b) {
+    const int64_t r0 = b * band, r1 = hs_min<int64_t>(n_rows, r0 + band);
+    k_csc_count<P><<<n_blocks, kConvThreads, smem, st>>>(cp, ri, n_rows, r0, r1, n_cols, cols_per_block, hist, flags);
+    HS_LAUNCH_CHECK(ctx);
+  }
   k_csc_offsets<<<(unsigned)((n_rows + 256) / 256), 256, 0, st>>>(hist, n_blocks, n_rows, total);
   HS_LAUNCH_CHECK(ctx);
   HS_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_ws, scan_ws, total, p_out, (int)(n_rows + 1), st));
   ctx->launches++;
   if (nnz > 0) {
-    k_csc_scatter<P, TI, TO><<<n_blocks, kConvThreads, smem, st>>>(cp, ri, x, n_rows, n_cols, cols_per_block, hist, p_out,
-                                                                  j_out, x_out);
-    HS_LAUNCH_CHECK(ctx);
+    for (int64_t b = 0; b < n_bands; ++b) {
+      const int64_t r0 = b * band, r1 = hs_min<int64_t>(n_rows, r0 + band);
+      k_csc_scatter<P, TI, TO><<<n_blocks, kConvThreads, smem, st>>>(cp, ri, x, n_rows, r0, r1, n_cols, cols_per_block, hist,
+                                                                    p_out, j_out, x_out);
+      HS_LAUNCH_CHECK(ctx);
+    }
   }
   int bad = 0;
   HS_CUDA(ctx, cudaMemcpyAsync(&bad, flags, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -108,7 +108,7 @@ def as_RsparseMatrix(m, rownames=None, colnames=None, ctx=None) -> dgRMatrix:
     With a DeviceContext `ctx`, a dgCMatrix is converted on the GPU (hs_csc_to_csr): same slots, bit for bit."""
     if isinstance(m, dgRMatrix):
         return m
-    if isinstance(m, dgCMatrix) and ctx is not None and m.Dim[0] <= 57344:
+    if isinstance(m, dgCMatrix) and ctx is not None:
         p, j, x = ctx.csc_to_csr(m.p, m.i, m.x, m.Dim[0], m.Dim[1])
         return dgRMatrix(p=p, j=j, x=x, Dim=m.Dim, rownames=rownames or m.rownames, colnames=colnames or m.colnames)
     if isinstance(m, dgCMatrix):

@@ -129,6 +129,8 @@ def test_csc_to_csr_matches_host_conversion(ctx, toy):
     a[250] = 1.5                     # a full row
     cases.append(sp_.as_CsparseMatrix(a))
     cases.append(sp_.as_CsparseMatrix(np.zeros((5, 7))))          # nothing stored
+    tall = rng.random((130_000, 24)) * (rng.random((130_000, 24)) < 0.06)     # more rows than one band of counters holds
+    cases.append(sp_.as_CsparseMatrix(tall))
     for m in cases:
         want = sp_.as_RsparseMatrix(m)
         got = sp_.as_RsparseMatrix(m, ctx=ctx)
