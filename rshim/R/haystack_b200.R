@@ -40,6 +40,12 @@ b200_randomize <- function(dev, expression, genes.to.randomize, randomization.co
                            draw = c("R", "device"), seed = sample.int(.Machine$integer.max, 1)) {
   draw <- match.arg(draw)
   n.sel <- length(genes.to.randomize)
+  if (is.matrix(expression) && draw == "device") {
+    # the whole loop :250-265 in one call; stream of (i, r) = (i - 1) * randomization.count + r - 1
+    storage.mode(expression) <- "double"
+    return(.Call("hsb_dkl_perm_dense_seeded_batch", dev, expression, as.integer(genes.to.randomize),
+                 as.integer(randomization.count), as.double(seed), PACKAGE = "haystackB200"))
+  }
   if (is.matrix(expression)) {
     out <- matrix(NA_real_, n.sel, randomization.count)
     for (i in seq_len(n.sel)) {

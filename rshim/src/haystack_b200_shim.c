@@ -135,6 +135,21 @@ SEXP hsb_dkl_perm_dense_seeded(SEXP sctx, SEXP v, SEXP n_perm, SEXP seed, SEXP s
   return out;
 }
 
+/* The whole dense loop R/haystack_continuous.R:250-265 in one call: rows sel (1-based, order of genes.to.randomize) of
+ * the genes x cells matrix; returns the n.genes.to.randomize x randomization.count matrix all.D_KL.randomized. */
+SEXP hsb_dkl_perm_dense_seeded_batch(SEXP sctx, SEXP expression, SEXP sel, SEXP n_perm, SEXP seed) {
+  hs_ctx* ctx = get_ctx(sctx);
+  const int64_t ld = (int64_t)nrows(expression), s = XLENGTH(sel);
+  const int r = asInteger(n_perm);
+  int64_t* rows = (int64_t*)R_alloc((size_t)s + 1, sizeof(int64_t));
+  for (int64_t i = 0; i < s; ++i) rows[i] = (int64_t)INTEGER(sel)[i] - 1;
+  SEXP out = PROTECT(allocMatrix(REALSXP, (int)s, r));
+  check(ctx, hs_dkl_perm_dense_seeded_batch(ctx, REAL(expression), ld, rows, s, r, (uint64_t)asReal(seed), 0, REAL(out)),
+        "hs_dkl_perm_dense_seeded_batch");
+  UNPROTECT(1);
+  return out;
+}
+
 /* Scores of all genes and the seeded randomization of rows sel (1-based, order of genes.to.randomize) in one
  * call; returns list(D_KL, all.D_KL.randomized). */
 SEXP hsb_dkl_csr_randomized(SEXP sctx, SEXP p, SEXP j, SEXP x, SEXP sel, SEXP n_perm, SEXP seed) {
@@ -175,6 +190,7 @@ static const R_CallMethodDef call_methods[] = {
     {"hsb_dkl_perm_csr", (DL_FUNC)&hsb_dkl_perm_csr, 5},
     {"hsb_dkl_perm_csr_seeded", (DL_FUNC)&hsb_dkl_perm_csr_seeded, 5},
     {"hsb_dkl_perm_dense_seeded", (DL_FUNC)&hsb_dkl_perm_dense_seeded, 5},
+    {"hsb_dkl_perm_dense_seeded_batch", (DL_FUNC)&hsb_dkl_perm_dense_seeded_batch, 5},
     {"hsb_dkl_csr_randomized", (DL_FUNC)&hsb_dkl_csr_randomized, 7},
     {"hsb_perm_sample", (DL_FUNC)&hsb_perm_sample, 4},
     {NULL, NULL, 0}};
