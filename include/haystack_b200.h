@@ -15,6 +15,17 @@
  *   hs_dkl_perm_csr       <- R/haystack_continuous.R:266-283  (sparse randomization loop)
  *   hs_dkl_perm_csr_seeded<- the same loop including its sample() call (:275), drawn on the device
  *   hs_dkl_perm_dense_seeded <- the dense loop including its sample() call (:259), drawn on the device
+ *                            (hs_dkl_perm_dense_seeded_batch: all selected genes in one call)
+ *   hs_dkl_csr_randomized <- :199-213 and :245-284 in one call (the randomization batch computes under the upload)
+ * and, around the path (optional; the host keeps them by default):
+ *   hs_row_stats_csr      <- R/haystack_continuous.R:57-74    (row means / sds)
+ *   hs_select_by_cv_dev   <- R/haystack_continuous.R:222, :227-236 (coeffVar, order(), the selected rows)
+ *   hs_csc_to_csr         <- R/haystack_continuous.R:113-116  (as(expression, "RsparseMatrix"))
+ *   hs_profile_csr/_dense <- R/haystack_continuous.R:604-666  (prepare_clustering)
+ *   hs_density_shard_*    <- :168-186 sharded over the cells of several ranks (three all-gathers by the host layer)
+ *   hs_r_*                <- base R's set.seed / unif_rand / sample.int / sample(prob=) / kmeans (Hartigan-Wong) on
+ *                            the host, bit for bit: what get_grid_points (R/haystack_highD.R:72-134), :259, :275 and
+ *                            :437 consume, for hosts without an R interpreter
  *
  * Conventions
  *   - Plain C, POD arguments only.  No R, torch or CUDA types in any signature.

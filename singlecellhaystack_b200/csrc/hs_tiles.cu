@@ -20,17 +20,19 @@
 //     share their cut, so each stored value lands in exactly one tile whatever the order inside a chunk;
 //     rows that are not ascending (or hold ids outside [0, N)) raise the flag that hands the call to the
 //     order-independent gather kernel (hs_contract.cu).
-//  2. k_tile_mma: one CTA per (pair of tile rows, cell segment).  Both tile rows share every density
-//     operand stage (halves the L2 traffic of the B operand).  Warp roles: 0 streams the entry chunks through
-//     small rings with cp.async.bulk, running ahead of the stages and prefetching the streams into L2; 1 issues
-//     the MMAs; 2-3 zero and scatter the A tiles (one tile row each; 2 also requests the stage's B tiles);
-//     4-19 drain TMEM.  Precision as in hs_umma.cu: x = hi + lo * 2^-11 for both operands,
-//     acc0 += A_hi D_hi is drained after every stage (the tensor core truncates each accumulating MMA;
-//     4 MMAs per sum keep that bias at the fp32 SIMT level), acc1 += A_hi D_lo + A_lo D_hi is 2^-11 smaller
-//     and stays in TMEM for a whole flush window.  fp32 register sums go to fp64 (L2 resident, single
-//     writer) every 32 stages.  The last CTA to finish a pair's segments runs the fp64 KL epilogue for its
-//     256 rows (segments added in fixed order: bit-identical repeats) -- no separate epilogue launch, no
-//     memset of the sums.
+//  2. k_tile_mma1 (default; k_tile_mma = the earlier form with two tile rows per CTA, HS_TILE_FORM=2): one CTA per
+//     (tile row, cell segment), three 64 KB operand stages, three acc0 buffers in TMEM.  Warp roles: 0-7 drain TMEM;
+//     8 streams the entry chunks through a small ring with cp.async.bulk, running ahead of the stages and prefetching
+//     the stream into L2; 9-12 scatter the entries into the A tiles (every warp takes its share of every chunk);
+//     13 issues the MMAs; 14 clears a released stage's A tiles and fetches its density tiles with bulk copies.
+//     Precision as in hs_umma.cu: x = hi + lo * 2^-11 for both operands, acc0 += A_hi D_hi is drained after every
+//     stage (the tensor core truncates each accumulating MMA; 4 MMAs per sum keep that bias at the fp32 SIMT level),
+//     acc1 += A_hi D_lo + A_lo D_hi is 2^-11 smaller and stays in TMEM for a whole flush window.  fp32 register sums
+//     go to fp64 (L2 resident, single writer) every 32 stages.  The last CTA to finish a tile row's segments runs the
+//     fp64 KL epilogue for its 128 rows (segments added in fixed order: bit-identical repeats) -- no separate epilogue
+//     launch, no memset of the sums.
+//  3. The seeded randomization (hs_run_perm_tiles, end of this file) skips step 1: the draw is written straight into
+//     fixed-capacity tile windows (k_perm_tile_draw) and the same MMA kernel scores them.
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
