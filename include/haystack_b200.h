@@ -152,6 +152,14 @@ int hs_dkl_perm_dense(hs_ctx* ctx, const double* v, const int32_t* perm, int n_p
 int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val,
                     const int32_t* ind, int n_perm, int index_base, double* out);
 
+/* Asynchronous pair of hs_dkl_perm_csr: _begin starts the call on a worker thread of the library and returns at once,
+ * so the host can draw the ids of the next batch (R's sample()) while this one is uploaded and scored; _wait blocks
+ * until it is done and writes the n_sel x n_perm result.  val and ind must stay valid until _wait returns (gene_ptr
+ * is copied).  One call in flight per context; every other entry point fails with HS_ERR_STATE until it is waited for. */
+int hs_dkl_perm_csr_begin(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val,
+                          const int32_t* ind, int n_perm, int index_base);
+int hs_dkl_perm_csr_wait(hs_ctx* ctx, double* out);
+
 int hs_dkl_perm_csr_f32(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const float* val,
                         const int32_t* ind, int n_perm, int index_base, double* out);
 

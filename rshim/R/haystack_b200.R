@@ -37,7 +37,7 @@ b200_dkl_csr <- function(dev, expression) {          # expression: dgRMatrix
 }
 
 b200_randomize <- function(dev, expression, genes.to.randomize, randomization.count, count.cells,
-                           draw = c("R", "device"), seed = sample.int(.Machine$integer.max, 1)) {
+                           draw = c("R", "device"), seed = sample.int(.Machine$integer.max, 1), batch.genes = 10L) {
   draw <- match.arg(draw)
   n.sel <- length(genes.to.randomize)
   if (is.matrix(expression) && draw == "device") {
@@ -72,19 +72,33 @@ b200_randomize <- function(dev, expression, genes.to.randomize, randomization.co
     return(.Call("hsb_dkl_perm_csr_seeded", dev, as.double(gene.ptr), unlist(vals),
                  as.integer(randomization.count), as.double(seed), PACKAGE = "haystackB200"))
   }
-  vals <- vector("list", n.sel); inds <- vector("list", n.sel)
-  for (i in seq_len(n.sel)) {
-    g <- genes.to.randomize[i]
-    lo <- expression@p[g] + 1L; hi <- expression@p[g + 1L]
-    nnz <- hi - lo + 1L
-    vals[[i]] <- if (nnz > 0) expression@x[lo:hi] else numeric(0)
-    # column r = sample(x = count.cells, size = nnz), as R/haystack_continuous.R:275
-    inds[[i]] <- as.integer(vapply(seq_len(randomization.count),
-                                   function(r) sample(x = count.cells, size = nnz), integer(nnz)))
+  # R draws the ids (in the reference's order: gene-major, randomization-minor) for one batch of genes while the
+  # previous batch is uploaded and scored (hs_dkl_perm_csr_begin / _wait)
+  out <- matrix(NA_real_, n.sel, randomization.count)
+  batches <- split(seq_len(n.sel), ceiling(seq_len(n.sel) / batch.genes))
+  in.flight <- NULL
+  for (b in batches) {
+    vals <- vector("list", length(b)); inds <- vector("list", length(b))
+    for (k in seq_along(b)) {
+      g <- genes.to.randomize[b[k]]
+      lo <- expression@p[g] + 1L; hi <- expression@p[g + 1L]
+      nnz <- hi - lo + 1L
+      vals[[k]] <- if (nnz > 0) expression@x[lo:hi] else numeric(0)
+      # column r = sample(x = count.cells, size = nnz), as R/haystack_continuous.R:275
+      inds[[k]] <- as.integer(vapply(seq_len(randomization.count),
+                                     function(r) sample(x = count.cells, size = nnz), integer(nnz)))
+    }
+    gene.ptr <- c(0, cumsum(vapply(vals, length, 0)))
+    if (length(batches) == 1L)      # nothing to overlap with: the blocking call
+      return(.Call("hsb_dkl_perm_csr", dev, as.double(gene.ptr), as.double(unlist(vals)), as.integer(unlist(inds)),
+                   as.integer(randomization.count), PACKAGE = "haystackB200"))
+    if (!is.null(in.flight)) out[in.flight, ] <- .Call("hsb_dkl_perm_csr_wait", dev, PACKAGE = "haystackB200")
+    .Call("hsb_dkl_perm_csr_begin", dev, as.double(gene.ptr), as.double(unlist(vals)), as.integer(unlist(inds)),
+          as.integer(randomization.count), PACKAGE = "haystackB200")
+    in.flight <- b
   }
-  gene.ptr <- c(0, cumsum(vapply(vals, length, 0)))
-  .Call("hsb_dkl_perm_csr", dev, as.double(gene.ptr), unlist(vals), unlist(inds),
-        as.integer(randomization.count), PACKAGE = "haystackB200")
+  if (!is.null(in.flight)) out[in.flight, ] <- .Call("hsb_dkl_perm_csr_wait", dev, PACKAGE = "haystackB200")
+  out
 }
 
 b200_perm_sample <- function(seed, stream, n, size)

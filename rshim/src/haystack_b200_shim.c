@@ -109,6 +109,49 @@ SEXP hsb_dkl_perm_csr(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP ind, SEXP n_perm)
   return out;
 }
 
+/* Asynchronous pair of hsb_dkl_perm_csr: _begin starts the scoring of one batch of genes on the library's worker
+ * thread and returns, so R can draw the next batch with sample() meanwhile; _wait returns the batch's
+ * n.genes x randomization.count matrix.  val and ind are read until the wait: they are preserved here and released
+ * there (the caller need not keep them alive). */
+static SEXP pending_val = NULL, pending_ind = NULL;
+static int64_t pending_rows = 0;
+static int pending_perm = 0;
+
+SEXP hsb_dkl_perm_csr_begin(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP ind, SEXP n_perm) {
+  hs_ctx* ctx = get_ctx(sctx);
+  if (pending_val) Rf_error("hsb_dkl_perm_csr_begin: a batch is already in flight");
+  const int64_t s = XLENGTH(gene_ptr) - 1;
+  const int r = asInteger(n_perm);
+  int64_t* gp = (int64_t*)R_alloc((size_t)s + 1, sizeof(int64_t));
+  for (int64_t i = 0; i <= s; ++i) gp[i] = (int64_t)REAL(gene_ptr)[i];
+  R_PreserveObject(val);
+  R_PreserveObject(ind);
+  const int rc = hs_dkl_perm_csr_begin(ctx, gp, s, REAL(val), INTEGER(ind), r, 1);
+  if (rc != HS_OK) {
+    R_ReleaseObject(val);
+    R_ReleaseObject(ind);
+    check(ctx, rc, "hs_dkl_perm_csr_begin");
+  }
+  pending_val = val;
+  pending_ind = ind;
+  pending_rows = s;
+  pending_perm = r;
+  return R_NilValue;
+}
+
+SEXP hsb_dkl_perm_csr_wait(SEXP sctx) {
+  hs_ctx* ctx = get_ctx(sctx);
+  if (!pending_val) Rf_error("hsb_dkl_perm_csr_wait: no batch in flight");
+  SEXP out = PROTECT(allocMatrix(REALSXP, (int)pending_rows, pending_perm));
+  const int rc = hs_dkl_perm_csr_wait(ctx, REAL(out));
+  R_ReleaseObject(pending_val);
+  R_ReleaseObject(pending_ind);
+  pending_val = pending_ind = NULL;
+  check(ctx, rc, "hs_dkl_perm_csr_wait");
+  UNPROTECT(1);
+  return out;
+}
+
 /* Seeded form: the draws of R/haystack_continuous.R:275 are made on the device.  seed: numeric(1) holding
  * a non-negative integer < 2^53 (e.g. sample.int(.Machine$integer.max, 1)). */
 SEXP hsb_dkl_perm_csr_seeded(SEXP sctx, SEXP gene_ptr, SEXP val, SEXP n_perm, SEXP seed) {
@@ -188,6 +231,8 @@ static const R_CallMethodDef call_methods[] = {
     {"hsb_dkl_csr", (DL_FUNC)&hsb_dkl_csr, 4},
     {"hsb_dkl_perm_dense", (DL_FUNC)&hsb_dkl_perm_dense, 3},
     {"hsb_dkl_perm_csr", (DL_FUNC)&hsb_dkl_perm_csr, 5},
+    {"hsb_dkl_perm_csr_begin", (DL_FUNC)&hsb_dkl_perm_csr_begin, 5},
+    {"hsb_dkl_perm_csr_wait", (DL_FUNC)&hsb_dkl_perm_csr_wait, 1},
     {"hsb_dkl_perm_csr_seeded", (DL_FUNC)&hsb_dkl_perm_csr_seeded, 5},
     {"hsb_dkl_perm_dense_seeded", (DL_FUNC)&hsb_dkl_perm_dense_seeded, 5},
     {"hsb_dkl_perm_dense_seeded_batch", (DL_FUNC)&hsb_dkl_perm_dense_seeded_batch, 5},

@@ -34,6 +34,8 @@ SIGNATURES = {
     "hs_dkl_dense": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_dkl_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp]),
     "hs_dkl_csr_f32": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _vp]),
+    "hs_dkl_perm_csr_begin": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int]),
+    "hs_dkl_perm_csr_wait": (_int, [_vp, _vp]),
     "hs_dkl_perm_csr_f32": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),
     "hs_dkl_perm_dense": (_int, [_vp, _vp, _vp, _int, _int, _vp]),
     "hs_dkl_perm_csr": (_int, [_vp, _vp, _i64, _vp, _vp, _int, _int, _vp]),

@@ -129,6 +129,18 @@ struct HostPool {
   int size() const { return (int)threads.size(); }
 };
 
+// One host-pointer call running on a worker thread of the library (hs_dkl_perm_csr_begin / hs_dkl_perm_csr_wait): the
+// caller's thread is free to draw the next batch of ids meanwhile.  The context stays single-user: every other entry
+// point refuses to run until the call has been waited for.
+struct HsAsync {
+  std::thread th;
+  std::thread::id worker;
+  bool pending = false;
+  int rc = HS_OK;
+  std::vector<int64_t> gene_ptr;
+  std::vector<double> result;
+};
+
 static int host_threads() {
   int n = (int)std::thread::hardware_concurrency();
   if (n <= 0) n = 1;
@@ -315,6 +327,8 @@ int need_density(hs_ctx* ctx) {
 }
 
 int set_device(hs_ctx* ctx) {
+  if (ctx->async && ctx->async->pending && std::this_thread::get_id() != ctx->async->worker)
+    return hs_fail(nullptr, HS_ERR_STATE, "an asynchronous call is in flight on this context: call hs_dkl_perm_csr_wait first");
   HS_CUDA(ctx, cudaSetDevice(ctx->device));
   return HS_OK;
 }
@@ -379,6 +393,11 @@ int hs_create(int device, hs_ctx** out) {
 
 void hs_destroy(hs_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->async) {
+    if (ctx->async->th.joinable()) ctx->async->th.join();
+    delete ctx->async;
+    ctx->async = nullptr;
+  }
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -948,6 +967,50 @@ int hs_dkl_perm_csr(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const d
                     int n_perm, int index_base, double* out) {
   try {
   return dkl_perm_csr_any(ctx, gene_ptr, n_sel, val, false, ind, n_perm, index_base, out);
+  } HS_ABI_CATCH(ctx)
+}
+
+// Asynchronous pair of hs_dkl_perm_csr: _begin starts the call on a worker thread and returns at once; _wait blocks
+// until it is done and delivers the result.  val and ind must stay valid until _wait returns (gene_ptr is copied).
+int hs_dkl_perm_csr_begin(hs_ctx* ctx, const int64_t* gene_ptr, int64_t n_sel, const double* val, const int32_t* ind,
+                          int n_perm, int index_base) {
+  try {
+  HS_TRY(need_density(ctx));
+  HS_TRY(set_device(ctx));
+  if (n_sel < 0 || n_perm <= 0 || !gene_ptr)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_begin: bad arguments");
+  if (!ctx->async) ctx->async = new HsAsync();
+  HsAsync* a = ctx->async;
+  if (a->th.joinable()) a->th.join();        // a finished call nobody waited for
+  a->gene_ptr.assign(gene_ptr, gene_ptr + n_sel + 1);
+  a->result.assign((size_t)(n_sel * (int64_t)n_perm), 0.0);
+  a->rc = HS_OK;
+  a->pending = true;
+  a->th = std::thread([ctx, a, n_sel, val, ind, n_perm, index_base] {
+    a->worker = std::this_thread::get_id();
+    try {
+      a->rc = dkl_perm_csr_any(ctx, a->gene_ptr.data(), n_sel, val, false, ind, n_perm, index_base, a->result.data());
+    } catch (const std::bad_alloc&) {
+      a->rc = hs_fail(ctx, HS_ERR_NOMEM, "out of host memory");
+    } catch (...) {
+      a->rc = hs_fail(ctx, HS_ERR_INVALID, "unexpected C++ exception in the asynchronous call");
+    }
+  });
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_dkl_perm_csr_wait(hs_ctx* ctx, double* out) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HsAsync* a = ctx->async;
+  if (!a || !a->pending) return hs_fail(ctx, HS_ERR_STATE, "hs_dkl_perm_csr_wait: no asynchronous call in flight");
+  if (a->th.joinable()) a->th.join();
+  a->pending = false;
+  if (a->rc != HS_OK) return a->rc;          // the worker left its message in the context
+  if (!out && !a->result.empty()) return hs_fail(ctx, HS_ERR_INVALID, "hs_dkl_perm_csr_wait: out is NULL");
+  if (!a->result.empty()) memcpy(out, a->result.data(), sizeof(double) * a->result.size());
+  return HS_OK;
   } HS_ABI_CATCH(ctx)
 }
 

@@ -91,6 +91,7 @@ struct hs_ctx {
   cudaEvent_t ev_ring[kRing] = {};   // the copy out of ring buffer k has finished
   bool ring_busy[kRing] = {};
   struct HostPool* pool = nullptr;
+  struct HsAsync* async = nullptr;   // hs_dkl_perm_csr_begin / _wait: the call in flight on the library's worker thread
 };
 
 // ---- error helpers (host) -----------------------------------------------------------------

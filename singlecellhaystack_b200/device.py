@@ -424,6 +424,35 @@ class DeviceContext:
                                               _ptr(out)), "hs_dkl_perm_csr")
         return out
 
+    def dkl_perm_csr_begin(self, vals: list, inds: list, index_base=1) -> None:
+        """hs_dkl_perm_csr_begin: start dkl_perm_csr(vals, inds) on the library's worker thread and return at once; the
+        host can draw the next batch meanwhile.  dkl_perm_csr_wait() delivers the result."""
+        s_ = len(vals)
+        r = inds[0].shape[1] if s_ else 1
+        gp = np.zeros(s_ + 1, dtype=np.int64)
+        for i, v in enumerate(vals):
+            if inds[i].shape != (len(v), r):
+                raise ValueError("inds[s] must be nnz_s x n_perm")
+            gp[i + 1] = gp[i] + len(v)
+        val = np.concatenate([np.asarray(v, dtype=np.float64) for v in vals]) if gp[-1] else np.zeros(0)
+        ind = (np.concatenate([np.asfortranarray(a, dtype=np.int32).ravel(order="F") for a in inds])
+               if gp[-1] else np.zeros(0, dtype=np.int32))
+        self._async_keep = (gp, val, ind, (s_, r))          # the library reads val / ind until the wait
+        self._check(self._lib.hs_dkl_perm_csr_begin(self._h, _ptr(gp), s_, _ptr(val), _ptr(ind), r, int(index_base)),
+                    "hs_dkl_perm_csr_begin")
+
+    def dkl_perm_csr_wait(self) -> np.ndarray:
+        """hs_dkl_perm_csr_wait: block until the call started by dkl_perm_csr_begin is done.  Returns (S, R)."""
+        keep = getattr(self, "_async_keep", None)
+        if keep is None:
+            raise RuntimeError("no asynchronous call in flight")
+        out = np.empty(keep[3], dtype=np.float64, order="F")
+        try:
+            self._check(self._lib.hs_dkl_perm_csr_wait(self._h, _ptr(out)), "hs_dkl_perm_csr_wait")
+        finally:
+            self._async_keep = None
+        return out
+
     def dkl_perm_csr_seeded(self, vals: list, n_perm: int, seed: int, stream_base: int = 0) -> np.ndarray:
         """hs_dkl_perm_csr_seeded: like dkl_perm_csr, but gene s / randomization r draws its cells on the
         device from the keyed permutation (seed, stream_base + s * n_perm + r); `perm_sample` returns the

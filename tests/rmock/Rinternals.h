@@ -37,6 +37,8 @@ SEXP R_MakeExternalPtr(void*, SEXP, SEXP);
 void* R_ExternalPtrAddr(SEXP);
 void R_ClearExternalPtr(SEXP);
 void R_RegisterCFinalizerEx(SEXP, R_CFinalizer_t, Rboolean);
+void R_PreserveObject(SEXP);
+void R_ReleaseObject(SEXP);
 
 #define PROTECT(x) (x)
 #define UNPROTECT(n) ((void)(n))

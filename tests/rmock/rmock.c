@@ -55,6 +55,9 @@ SEXP R_MakeExternalPtr(void* p, SEXP tag, SEXP prot) {
 void* R_ExternalPtrAddr(SEXP s) { return s->data; }
 void R_ClearExternalPtr(SEXP s) { s->data = NULL; }
 void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t f, Rboolean onexit) { (void)onexit; s->finalizer = f; }
+int rmock_preserved = 0;   /* objects held by R_PreserveObject and not yet released */
+void R_PreserveObject(SEXP s) { (void)s; ++rmock_preserved; }
+void R_ReleaseObject(SEXP s) { (void)s; --rmock_preserved; }
 
 static DllInfo the_dll;
 int R_registerRoutines(DllInfo* d, const void* c, const R_CallMethodDef* call, const void* f, const void* e) {

@@ -43,6 +43,15 @@ def test_shim_routines_match_the_c_abi(ctx, toy):
     np.testing.assert_array_equal(got, ctx.dkl_perm_csr(vals, inds, index_base=1))
     want_r = ho.dkl_randomized_sparse(vals, [a.T for a in inds], ho.density_stage(xs, grid)["density"], want["Q"])
     np.testing.assert_allclose(got, want_r, rtol=1e-5)
+    # the asynchronous pair: same numbers; a second begin before the wait and a wait without a begin are R errors
+    args = (dev, sh.real(gp), sh.real(np.concatenate(vals)),
+            sh.integer(np.concatenate([a.ravel(order="F") for a in inds])), sh.integer([4]))
+    sh.call("hsb_dkl_perm_csr_begin", *args)
+    with pytest.raises(RError, match="already in flight"):
+        sh.call("hsb_dkl_perm_csr_begin", *args)
+    np.testing.assert_array_equal(sh.to_numpy(sh.call("hsb_dkl_perm_csr_wait", dev)), got)
+    with pytest.raises(RError, match="no batch in flight"):
+        sh.call("hsb_dkl_perm_csr_wait", dev)
     # one call for scores + seeded randomization; ids reproducible on the R side
     out = sh.to_numpy(sh.call("hsb_dkl_csr_randomized", dev, sh.integer(sp.p), sh.integer(sp.j), sh.real(sp.x),
                               sh.integer(np.array(rows) + 1), sh.integer([4]), sh.real([123.0])))

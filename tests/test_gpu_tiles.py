@@ -186,3 +186,34 @@ def test_packed_id_upload_is_transparent(ctx, monkeypatch):
     ok[1500] = False
     np.testing.assert_array_equal(swapped[ok], plain[ok])
     assert abs(swapped[1500] - plain[1500]) <= 2e-5 * abs(plain[1500])      # scored by the gather kernel
+
+
+def test_begin_wait_pair_overlaps_host_work(ctx, toy):
+    """hs_dkl_perm_csr_begin / _wait: the same scores as the blocking call; the context refuses other work while a call
+    is in flight; batches can be pipelined (draw the next ids while the previous batch is scored)."""
+    from singlecellhaystack_b200.device import HaystackLibraryError
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    ctx.density(xs, toy["grid100"])
+    rng = np.random.default_rng(9)
+    n = 601
+
+    def batch(k):
+        vals = [rng.gamma(2.0, 1.0, size=int(s)) for s in rng.integers(1, 400, size=k)]
+        inds = [np.asfortranarray(np.stack([rng.permutation(n)[:v.size] + 1 for _ in range(6)]).T.astype(np.int32)) for v in vals]
+        return vals, inds
+
+    b0, b1 = batch(5), batch(7)
+    want0, want1 = ctx.dkl_perm_csr(*b0), ctx.dkl_perm_csr(*b1)
+    ctx.dkl_perm_csr_begin(*b0)
+    with pytest.raises(HaystackLibraryError):              # single user: nothing else may run on the context now
+        ctx.dkl_perm_csr(*b1)
+    got0 = ctx.dkl_perm_csr_wait()
+    np.testing.assert_array_equal(got0, want0)
+    # pipelined: begin(b1), prepare the next batch on this thread, wait
+    ctx.dkl_perm_csr_begin(*b1)
+    b2 = batch(3)
+    got1 = ctx.dkl_perm_csr_wait()
+    np.testing.assert_array_equal(got1, want1)
+    np.testing.assert_array_equal(ctx.dkl_perm_csr(*b2), ctx.dkl_perm_csr(*b2))
+    with pytest.raises(HaystackLibraryError, match="no asynchronous call"):
+        ctx._check(ctx._lib.hs_dkl_perm_csr_wait(ctx._h, None), "hs_dkl_perm_csr_wait")
