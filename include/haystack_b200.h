@@ -260,6 +260,19 @@ int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, 
 int hs_select_by_cv_dev(hs_ctx* ctx, const double* mean_dev, const double* sd_dev, int64_t n_genes,
                         const int64_t* ranks, int64_t n_ranks, double* cv_dev_out, int64_t* rows_out);
 
+/* ---- grid selection, "seeding" method (the step before the path; optional) ------------------------------------ */
+/* get_grid_points(method = "seeding") (R/haystack_highD.R:87-129) is a chain of distance passes over all cells with a
+ * weighted draw between them.  The passes run here; the draws -- sample(N, 1) (:95) and sample(N, 1, prob = probs)
+ * (:110) -- stay with the caller, who owns the random stream:
+ *   hs_grid_seed_begin(x)        uploads the (scaled) coordinates, N x d column-major; min.dist.to.grid := Inf
+ *   hs_grid_seed_step(index, probs_out, nearest3_out)   the cell `index` (0-based) becomes the next grid point:
+ *        tmp = distances of all cells to it (:113), min.dist.to.grid = pmin(min.dist.to.grid, tmp) (:116);
+ *        probs_out (host, N doubles, or NULL) = min.dist.to.grid^2, the weights of the NEXT draw (:107);
+ *        nearest3_out (host, 3 x int64, 0-based, -1 when N < 3) = order(tmp)[1:3], the cells whose weighted mean
+ *        (weights 2, 1, 1) replaces the grid point at the end (:124-128).  Needs no density state. */
+int hs_grid_seed_begin(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims);
+int hs_grid_seed_step(hs_ctx* ctx, int64_t index, double* probs_out, int64_t* nearest3_out);
+
 /* ---- CSC -> CSR (the step before the sparse path; optional) -------------------------------- */
 /* as(expression, "RsparseMatrix") (R/haystack_continuous.R:113-116) on the device: a stable counting sort by
  * row id, column ids ascending inside every row, bit-reproducible.  cp: column pointers of the dgCMatrix

@@ -61,6 +61,8 @@ SIGNATURES = {
     "hs_profile_dense": (_int, [_vp, _vp, _i64, _i64, _vp]),
     "hs_row_stats_csr": (_int, [_vp, _vp, _int, _vp, _i64, _i64, _vp, _vp]),
     "hs_row_stats_csr_dev": (_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "hs_grid_seed_begin": (_int, [_vp, _vp, _i64, _int]),
+    "hs_grid_seed_step": (_int, [_vp, _i64, _vp, _vp]),
     "hs_select_by_cv_dev": (_int, [_vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "hs_csc_to_csr": (_int, [_vp, _vp, _int, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     "hs_csc_to_csr_dev": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),

@@ -1497,6 +1497,44 @@ int hs_row_stats_csr_dev(hs_ctx* ctx, const int64_t* p_dev, const float* x_dev, 
   } HS_ABI_CATCH(ctx)
 }
 
+// ---- grid selection, "seeding" method (R/haystack_highD.R:87-129) ------------------------------------------------
+int hs_grid_seed_begin(hs_ctx* ctx, const double* x, int64_t n_cells, int n_dims) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (!x || n_cells <= 0 || n_dims <= 0 || n_dims > 4096)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_grid_seed_begin: bad arguments");
+  HS_TRY(hs_ensure(ctx, ctx->xin, sizeof(double) * (size_t)n_cells * (size_t)n_dims));
+  HS_CUDA(ctx, cudaMemcpyAsync(ctx->xin.p, x, sizeof(double) * (size_t)n_cells * (size_t)n_dims, cudaMemcpyHostToDevice,
+                               ctx->stream));
+  HS_TRY(hs_run_seed_begin(ctx, n_cells, n_dims));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->seed_n = n_cells;
+  ctx->seed_d = n_dims;
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
+int hs_grid_seed_step(hs_ctx* ctx, int64_t index, double* probs_out, int64_t* nearest3_out) {
+  try {
+  if (!ctx) return hs_fail(nullptr, HS_ERR_INVALID, "null context");
+  HS_TRY(set_device(ctx));
+  if (ctx->seed_n <= 0) return hs_fail(ctx, HS_ERR_STATE, "hs_grid_seed_step: call hs_grid_seed_begin first");
+  if (index < 0 || index >= ctx->seed_n || !nearest3_out)
+    return hs_fail(ctx, HS_ERR_INVALID, "hs_grid_seed_step: bad arguments");
+  const double* probs_dev = nullptr;
+  const void* near_dev = nullptr;
+  HS_TRY(hs_run_seed_step(ctx, (const double*)ctx->xin.p, ctx->seed_n, ctx->seed_d, index, &probs_dev, &near_dev));
+  struct { double d; long long c; } h[3];
+  HS_CUDA(ctx, cudaMemcpyAsync(h, near_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  if (probs_out)
+    HS_CUDA(ctx, cudaMemcpyAsync(probs_out, probs_dev, sizeof(double) * (size_t)ctx->seed_n, cudaMemcpyDeviceToHost, ctx->stream));
+  HS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int r = 0; r < 3; ++r) nearest3_out[r] = (r < ctx->seed_n) ? (int64_t)h[r].c : -1;
+  return HS_OK;
+  } HS_ABI_CATCH(ctx)
+}
+
 // coeffVar and the rows at the given ranks of order(coeffVar) from device-resident row statistics; see hs_spmm.cu
 int hs_select_by_cv_dev(hs_ctx* ctx, const double* mean_dev, const double* sd_dev, int64_t n_genes, const int64_t* ranks,
                         int64_t n_ranks, double* cv_dev_out, int64_t* rows_out) {

@@ -91,6 +91,8 @@ struct hs_ctx {
   cudaEvent_t ev_ring[kRing] = {};   // the copy out of ring buffer k has finished
   bool ring_busy[kRing] = {};
   struct HostPool* pool = nullptr;
+  int64_t seed_n = 0;      // hs_grid_seed_*: cells / dims of the coordinates resident in xin
+  int seed_d = 0;
   struct HsAsync* async = nullptr;   // hs_dkl_perm_csr_begin / _wait: the call in flight on the library's worker thread
 };
 
@@ -125,6 +127,10 @@ int hs_ensure(hs_ctx* ctx, DevBuf& b, size_t bytes);
 // density stage (hs_density.cu): inputs device-resident fp64 column-major
 int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const double* grid_dev, int G,
                    const double* wq_dev, bool want_dens64);
+// grid selection, "seeding" method: the distance passes (hs_density.cu)
+int hs_run_seed_begin(hs_ctx* ctx, int64_t N, int d);
+int hs_run_seed_step(hs_ctx* ctx, const double* x_dev, int64_t N, int d, int64_t index, const double** probs_dev_out,
+                     const void** nearest_dev_out);
 // contraction kernels (hs_contract.cu)
 // slab-staged sparse contraction (hs_spmm.cu); see there for the arguments
 int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_units, int n_perm,

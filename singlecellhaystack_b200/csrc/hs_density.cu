@@ -321,3 +321,145 @@ int hs_run_density(hs_ctx* ctx, const double* x_dev, int64_t N, int d, const dou
   HS_TRY(hs_density_step_dens(ctx, N, G, wq_dev, 0, N, want_dens64));
   return hs_density_step_q(ctx, N, G);
 }
+
+// =================================================================================================================
+// Grid selection, "seeding" method (R/haystack_highD.R:87-129): the K1-like passes on the device.
+//   per new grid point (cell `index`):  tmp = get_dist_two_sets(input, grid[i, ])            :113
+//                                       min.dist.to.grid = pmin(min.dist.to.grid, tmp)       :116
+//                                       probs = min.dist.to.grid^2 (of the NEXT iteration)   :107
+//                                       order(tmp)[1:3]: the three cells nearest to the new grid point, which the
+//                                       final averaging (:124-128) replaces it by (ties: lower cell first)
+// The weighted draw sample(N, 1, prob = probs) (:110) stays with the host: it consumes R's random stream.
+// =================================================================================================================
+namespace {
+
+struct Near { double d; long long c; };
+__device__ __forceinline__ bool near_less(const Near& a, const Near& b) { return a.d < b.d || (a.d == b.d && a.c < b.c); }
+__device__ __forceinline__ Near near_min(Near a, Near b) { return near_less(b, a) ? b : a; }
+
+// the three smallest (distance, cell) pairs of a block's values -> out[3]
+__device__ void block_three_nearest(Near mine, Near* out) {
+  __shared__ Near wbest[32];
+  __shared__ Near pick;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  for (int r = 0; r < 3; ++r) {
+    Near v = mine;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      Near u;
+      u.d = __shfl_xor_sync(0xffffffffu, v.d, o);
+      u.c = __shfl_xor_sync(0xffffffffu, v.c, o);
+      v = near_min(v, u);
+    }
+    if (lane == 0) wbest[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      Near w = lane < nw ? wbest[lane] : Near{INFINITY, 0x7fffffffffffffffLL};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        Near u;
+        u.d = __shfl_xor_sync(0xffffffffu, w.d, o);
+        u.c = __shfl_xor_sync(0xffffffffu, w.c, o);
+        w = near_min(w, u);
+      }
+      if (lane == 0) {
+        pick = w;
+        out[r] = w;
+      }
+    }
+    __syncthreads();
+    if (mine.c == pick.c) mine = Near{INFINITY, 0x7fffffffffffffffLL};      // taken
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_seed_step(const double* __restrict__ x, int64_t N, int d, int64_t index, double* __restrict__ min_dist,
+            double* __restrict__ probs, Near* __restrict__ cand) {
+  extern __shared__ double xi[];      // coordinates of the new grid point
+  for (int k = threadIdx.x; k < d; k += blockDim.x) xi[k] = x[index + (int64_t)k * N];
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Near mine{INFINITY, 0x7fffffffffffffffLL};
+  if (c < N) {
+    double acc = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double diff = x[c + (int64_t)k * N] - xi[k];
+      acc = __dadd_rn(acc, __dmul_rn(diff, diff));      // (x - y)^2 summed in order, no contraction
+    }
+    const double dist = sqrt(acc);
+    const double mn = fmin(min_dist[c], dist);
+    min_dist[c] = mn;
+    probs[c] = mn * mn;
+    mine = Near{dist, (long long)c};
+  }
+  block_three_nearest(mine, cand + 3 * (size_t)blockIdx.x);
+}
+
+__global__ void __launch_bounds__(256)
+k_seed_nearest(const Near* __restrict__ cand, int64_t n_cand, Near* __restrict__ out) {
+  // the three smallest of all block candidates; candidates are distinct cells
+  Near best[3] = {{INFINITY, 0x7fffffffffffffffLL}, {INFINITY, 0x7fffffffffffffffLL}, {INFINITY, 0x7fffffffffffffffLL}};
+  __shared__ Near stage[3 * 256];
+  for (int64_t i = threadIdx.x; i < n_cand; i += blockDim.x) {
+    Near v = cand[i];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      if (near_less(v, best[r])) {
+        const Near t = best[r];
+        best[r] = v;
+        v = t;
+      }
+  }
+  for (int r = 0; r < 3; ++r) stage[3 * threadIdx.x + r] = best[r];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    Near top[3] = {{INFINITY, 0x7fffffffffffffffLL}, {INFINITY, 0x7fffffffffffffffLL}, {INFINITY, 0x7fffffffffffffffLL}};
+    for (int i = 0; i < 3 * (int)blockDim.x; ++i) {
+      Near v = stage[i];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+        if (near_less(v, top[r])) {
+          const Near t = top[r];
+          top[r] = v;
+          v = t;
+        }
+    }
+    for (int r = 0; r < 3; ++r) out[r] = top[r];
+  }
+}
+
+__global__ void k_fill_inf(double* __restrict__ a, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = INFINITY;
+}
+
+}  // namespace
+
+// x_dev: N x d fp64 column-major, resident for the whole selection (ctx->xin); min distances start at +Inf
+int hs_run_seed_begin(hs_ctx* ctx, int64_t N, int d) {
+  HS_TRY(hs_ensure(ctx, ctx->rowmin, sizeof(double) * (size_t)N));
+  HS_TRY(hs_ensure(ctx, ctx->sq, sizeof(double) * (size_t)N));
+  const int64_t n_blocks = (N + 255) / 256;
+  HS_TRY(hs_ensure(ctx, ctx->qpart, sizeof(Near) * (size_t)(3 * n_blocks + 3)));
+  k_fill_inf<<<(unsigned)n_blocks, 256, 0, ctx->stream>>>((double*)ctx->rowmin.p, N);
+  HS_LAUNCH_CHECK(ctx);
+  (void)d;
+  return HS_OK;
+}
+
+// one new grid point = cell `index`: min distances and probs updated (probs_dev_out = ctx->sq), the three nearest cells
+// of the new point written to nearest_dev (3 x {distance, cell})
+int hs_run_seed_step(hs_ctx* ctx, const double* x_dev, int64_t N, int d, int64_t index, const double** probs_dev_out,
+                     const void** nearest_dev_out) {
+  const int64_t n_blocks = (N + 255) / 256;
+  Near* cand = (Near*)ctx->qpart.p;
+  k_seed_step<<<(unsigned)n_blocks, 256, sizeof(double) * (size_t)d, ctx->stream>>>(x_dev, N, d, index, (double*)ctx->rowmin.p,
+                                                                                 (double*)ctx->sq.p, cand);
+  HS_LAUNCH_CHECK(ctx);
+  k_seed_nearest<<<1, 256, 0, ctx->stream>>>(cand, 3 * n_blocks, cand + 3 * n_blocks);
+  HS_LAUNCH_CHECK(ctx);
+  *probs_dev_out = (const double*)ctx->sq.p;
+  *nearest_dev_out = cand + 3 * n_blocks;
+  return HS_OK;
+}

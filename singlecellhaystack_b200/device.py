@@ -166,6 +166,25 @@ class DeviceContext:
         self._check(self._lib.hs_row_stats_csr_dev(self._h, _dptr(p_dev), _dptr(x_dev), p_dev.numel() - 1, int(n_cells),
                                                    _dptr(mean_dev), _dptr(sd_dev)), "hs_row_stats_csr_dev")
 
+    # -- grid selection, "seeding" method (R/haystack_highD.R:87-129) ---------------------------
+    def grid_seed_begin(self, x) -> None:
+        """hs_grid_seed_begin: coordinates (N, d) resident for the distance passes of the seeding method."""
+        x = _f64_colmajor(x, "x")
+        if x.ndim == 1:
+            x = x.reshape(-1, 1, order="F")
+        self._seed_n = int(x.shape[0])
+        self._check(self._lib.hs_grid_seed_begin(self._h, _ptr(x), int(x.shape[0]), int(x.shape[1])), "hs_grid_seed_begin")
+
+    def grid_seed_step(self, index: int, want_probs: bool = True):
+        """hs_grid_seed_step: cell `index` (0-based) becomes a grid point.  Returns (probs, nearest3): the weights
+        min.dist.to.grid^2 of the next draw (None unless wanted) and the 0-based ids of the three cells nearest to the
+        new grid point."""
+        probs = np.empty(self._seed_n, dtype=np.float64) if want_probs else None
+        near = np.empty(3, dtype=np.int64)
+        self._check(self._lib.hs_grid_seed_step(self._h, int(index), _ptr(probs) if probs is not None else None, _ptr(near)),
+                    "hs_grid_seed_step")
+        return probs, near[near >= 0]
+
     def select_by_cv(self, mean, sd, ranks, return_cv=False):
         """hs_select_by_cv_dev: rows at the 0-based `ranks` of order(coeffVar), coeffVar = (sd + 1e-300) / (mean + 1e-300)
         (R/haystack_continuous.R:222, :227-236) -- sorted on the device.  mean / sd: the row statistics WITHOUT the

@@ -62,8 +62,9 @@ def _kmeans_lloyd(x: np.ndarray, k: int, iter_max: int, nstart: int, rng: np.ran
     return best
 
 
-def get_grid_points(input, method: str = "centroid", grid_points: int = 100, rng=None) -> np.ndarray:
-    """R/haystack_highD.R:72-134.  Returns (grid.points, d) coordinates."""
+def get_grid_points(input, method: str = "centroid", grid_points: int = 100, rng=None, ctx=None) -> np.ndarray:
+    """R/haystack_highD.R:72-134.  Returns (grid.points, d) coordinates.  With a device context `ctx` the distance
+    passes of the "seeding" method run on the GPU (hs_grid_seed_*); the draws stay here, on `rng`."""
     x = np.asarray(input, dtype=np.float64)
     r_stream = rng if hasattr(rng, "kmeans") and hasattr(rng, "sample_prob_one") else None     # rcompat.RRandom
     if r_stream is None:
@@ -75,6 +76,20 @@ def get_grid_points(input, method: str = "centroid", grid_points: int = 100, rng
         if r_stream is not None:           # R's own kmeans(): Hartigan-Wong on R's random stream
             return r_stream.kmeans(x, int(grid_points), iter_max=10, nstart=10)
         return _kmeans_lloyd(x, int(grid_points), iter_max=10, nstart=10, rng=rng)
+    if method == "seeding" and ctx is not None:                                       # :87-129, distances on the device
+        n, d = x.shape
+        w = np.array([2.0, 1.0, 1.0])                                                 # :124
+        grid = np.full((grid_points, d), np.nan)
+        ctx.grid_seed_begin(x)
+        index = int(r_stream.sample_int(n, 1)[0]) - 1 if r_stream is not None else int(rng.integers(n))   # :95
+        for i in range(grid_points):
+            probs, o = ctx.grid_seed_step(index, want_probs=i + 1 < grid_points)
+            ww = w[:o.size]
+            grid[i] = (x[o] * ww[:, None]).sum(axis=0) / ww.sum()                     # :127 weighted.mean of order(tmp)[1:3]
+            if i + 1 < grid_points:                                                   # :107-110
+                index = (r_stream.sample_prob_one(probs) - 1 if r_stream is not None
+                         else int(rng.choice(n, p=probs / probs.sum())))
+        return grid
     if method == "seeding":                                                           # :87-129
         n, d = x.shape
         grid = np.full((grid_points, d), np.nan)

@@ -305,16 +305,19 @@ def haystack_continuous_highD(x, expression, grid_points=100, weights_advanced_Q
         rng = np.random.default_rng(rng)
     elif perm_source is None:
         perm_source = r_stream.perm_source
-    if grid_coord is None:
-        _message(verbose, "### deciding grid points...")
-        grid_coord = _grid.get_grid_points(x, method=grid_method, grid_points=int(grid_points), rng=rng)
-        if grid_coord.shape[0] != grid_points:
-            warnings.warn(f"The number of grid points was changed from {grid_points} to {grid_coord.shape[0]}")
-            grid_points = grid_coord.shape[0]
-
     if ctx is None:
         ctx, own_ctx = DeviceContext(device), True
     try:
+        if grid_coord is None:
+            _message(verbose, "### deciding grid points...")
+            # "seeding": the distance passes run on the device (hs_grid_seed_*), the draws stay on `rng`;
+            # "centroid" is kmeans() on the host (Hartigan-Wong with rcompat.RRandom)
+            grid_coord = _grid.get_grid_points(x, method=grid_method, grid_points=int(grid_points), rng=rng,
+                                               ctx=ctx if grid_method == "seeding" else None)
+            if grid_coord.shape[0] != grid_points:
+                warnings.warn(f"The number of grid points was changed from {grid_points} to {grid_coord.shape[0]}")
+                grid_points = grid_coord.shape[0]
+
         # ---- K1: density stage on the device (:168-186) -----------------------------------
         dens = ctx.density(x, grid_coord, w_q=weights_advanced_Q, want_densities=return_densities)
 

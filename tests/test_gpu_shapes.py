@@ -200,3 +200,30 @@ def test_gene_selection_on_the_device(ctx):
     from singlecellhaystack_b200.device import HaystackLibraryError
     with pytest.raises(HaystackLibraryError, match="outside"):
         ctx.select_by_cv(mean, sd, np.array([10]))
+
+
+def test_seeding_grid_with_device_distances(ctx, toy):
+    """get_grid_points(method = "seeding") (R/haystack_highD.R:87-129) with the distance passes on the device
+    (hs_grid_seed_*): the same picks and the same grid as the host computation, on R's stream and on numpy's; and as
+    the oracle's restatement of the R procedure."""
+    from oracle import r_base
+    from singlecellhaystack_b200 import grid as gr
+    from singlecellhaystack_b200.rcompat import RRandom
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    for g in (7, 60):
+        host = gr.get_grid_points(xs, "seeding", g, rng=RRandom(1234))
+        dev = gr.get_grid_points(xs, "seeding", g, rng=RRandom(1234), ctx=ctx)
+        np.testing.assert_allclose(dev, host, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(dev, r_base.get_grid_points(xs, r_base.RRng(1234), "seeding", g), rtol=0, atol=1e-12)
+        host_np = gr.get_grid_points(xs, "seeding", g, rng=5)
+        dev_np = gr.get_grid_points(xs, "seeding", g, rng=5, ctx=ctx)
+        np.testing.assert_allclose(dev_np, host_np, rtol=0, atol=1e-12)
+    # a bigger cloud in 20 dimensions, duplicated cells (tied distances: the lower cell id wins, as order() does)
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(20000, 20))
+    x[100:110] = x[50]
+    np.testing.assert_allclose(gr.get_grid_points(x, "seeding", 25, rng=11, ctx=ctx),
+                               gr.get_grid_points(x, "seeding", 25, rng=11), rtol=0, atol=1e-12)
+    # fewer than three cells
+    tiny = rng.normal(size=(2, 3))
+    np.testing.assert_allclose(gr.get_grid_points(tiny, "seeding", 2, rng=1, ctx=ctx), gr.get_grid_points(tiny, "seeding", 2, rng=1))
