@@ -753,14 +753,14 @@ def run_e2e(a, w, shard, ctx, world, rank, dev, value_dtype="float64", pinned=Tr
     p_h = w.p[:m_e2e + 1].cpu()
     nnz_e = int(p_h[-1])
     # fp64 host values are narrowed to fp32 by the library's host threads before they cross PCIe (unless the rank has
-    # four host threads or fewer to itself, or HS_NARROW_ON_DEVICE=1; hs_api.cu: host_threads()): count the bytes
-    # that are actually copied
+    # four host threads or fewer to itself, three or more ranks share the node, or HS_NARROW_ON_DEVICE=1; hs_api.cu):
+    # count the bytes that are actually copied
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
     threads = min(16, max(1, (os.cpu_count() or 1) // max(local_world, 1)))
     if os.environ.get("HS_HOST_THREADS", "").isdigit() and int(os.environ["HS_HOST_THREADS"]) > 0:
         threads = int(os.environ["HS_HOST_THREADS"])
     nod = os.environ.get("HS_NARROW_ON_DEVICE")
-    narrow_dev = (nod not in (None, "", "0")) if nod is not None else threads <= 4
+    narrow_dev = (nod not in (None, "", "0")) if nod is not None else (threads <= 4 or local_world >= 3)
     vbytes = 8.0 if (value_dtype == "float64" and narrow_dev) else 4.0
     j_t, j_np = _host_buffer(nnz_e, torch.int32, pinned)
     j_t.copy_(w.cols[:nnz_e])

@@ -141,6 +141,13 @@ struct HsAsync {
   std::vector<double> result;
 };
 
+// processes of this job on this node (torchrun exports LOCAL_WORLD_SIZE); 1 when not launched that way
+static int local_ranks() {
+  const char* e = getenv("LOCAL_WORLD_SIZE");
+  const int lw = e ? atoi(e) : 1;
+  return lw > 1 ? lw : 1;
+}
+
 static int host_threads() {
   int n = (int)std::thread::hardware_concurrency();
   if (n <= 0) n = 1;
@@ -612,8 +619,11 @@ static int upload_and_run(hs_ctx* ctx, const int64_t* hp, int64_t n_units, const
   // a kernel (HS_NARROW_ON_DEVICE=1); both give the same fp32 bits
   // (with four host threads or fewer per rank the host is the bottleneck: the doubles cross the link and a kernel
   //  narrows them.  Measured with eight ranks on a 32-core host, 30 000 genes over all ranks: 363 ms per step narrowing
-  //  on the host, 288 ms splitting the chunks between host and device, 238 ms narrowing on the device.)
-  const bool narrow_on_device = getenv("HS_NARROW_ON_DEVICE") ? env_size("HS_NARROW_ON_DEVICE", 0) != 0 : host_threads() <= 4;
+  //  on the host, 288 ms splitting the chunks between host and device, 238 ms narrowing on the device.  The ranks of a
+  //  node also share its DRAM: host narrowing moves 20 bytes of host memory per value, the plain upload 12 -- four
+  //  ranks on 32 cores: 398 ms narrowing on the host, 251 ms on the device; two ranks: 456 against 444 ms, a wash.)
+  const bool narrow_on_device = getenv("HS_NARROW_ON_DEVICE") ? env_size("HS_NARROW_ON_DEVICE", 0) != 0
+                                                              : (host_threads() <= 4 || local_ranks() >= 3);
   // R vectors (and numpy arrays) are pageable: their ids are bounced through the pinned ring by the host threads,
   // like the values, instead of being handed to cudaMemcpyAsync directly (HS_NO_ID_BOUNCE=1: old behaviour)
   const bool bounce_ids = !perm && !narrow_on_device && is_pageable(ids) && env_size("HS_NO_ID_BOUNCE", 0) == 0;
