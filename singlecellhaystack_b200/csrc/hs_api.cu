@@ -413,7 +413,7 @@ void hs_destroy(hs_ctx* ctx) {
                     &ctx->stage_j[0], &ctx->stage_j[1], &ctx->stage_x[0], &ctx->stage_x[1], &ctx->vals32,
                     &ctx->ptrs, &ctx->spmm_ws, &ctx->spmm_slots, &ctx->cols32, &ctx->dtile_hi, &ctx->dtile_lo, &ctx->umma_flags, &ctx->dense32, &ctx->simt_part, &ctx->perm_rp, &ctx->perm_cols, &ctx->perm_vals, &ctx->perm_gp, &ctx->out_rand,
                     &ctx->tile_ent, &ctx->tile_ws, &ctx->prof_x, &ctx->prof_out, &ctx->conv_cp, &ctx->conv_ri, &ctx->conv_x, &ctx->conv_p, &ctx->conv_j, &ctx->conv_xo,
-                    &ctx->bits[0], &ctx->bits[1], &ctx->zeros, &ctx->dbg_times};
+                    &ctx->bits[0], &ctx->bits[1], &ctx->zeros, &ctx->dbg_times, &ctx->conv_sort};
   for (DevBuf* b : bufs) hs_free(*b);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (int k = 0; k < hs_ctx::kRing; ++k) {

@@ -80,6 +80,7 @@ struct hs_ctx {
   DevBuf dense32;              // uploaded dense expression as fp32 (column-major, ld = rows)
   DevBuf perm_rp, perm_cols, perm_vals;   // randomization batch: row pointers, (id, value) pairs, values of the selected rows
   DevBuf conv_cp, conv_ri, conv_x, conv_p, conv_j, conv_xo;   // hs_csc_to_csr (host form): inputs and outputs
+  DevBuf conv_sort;            // hs_csc_to_csr on large inputs: records, sort buffers, per-chunk row offsets
   DevBuf perm_gp, out_rand;               // hs_dkl_csr_randomized: gene pointers and results of the randomization batch
   bool skip_copy_fence = false;           // the caller guarantees that nothing in flight reads the upload buffers
   void* pinned = nullptr;      // small pinned host bounce buffer

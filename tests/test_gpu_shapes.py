@@ -1,5 +1,7 @@
 """Shape sweep of the device path against the oracle: grid sizes that select every kernel variant
 (1, 2, 4, 8 float4 per lane; tensor-core and SIMT dense kernels), tiny and ragged inputs."""
+import os
+
 import numpy as np
 import pytest
 
@@ -137,6 +139,16 @@ def test_csc_to_csr_matches_host_conversion(ctx, toy):
         np.testing.assert_array_equal(got.p, want.p)
         np.testing.assert_array_equal(got.j, want.j)
         np.testing.assert_array_equal(got.x, want.x)
+        # large inputs are placed by a stable radix sort, chunk of column blocks by chunk: forced here, small chunks
+        for chunk in ("1000000000", "5000", "1024"):
+            os.environ["HS_CONVERT_SORT"], os.environ["HS_CONVERT_CHUNK"] = "1", chunk
+            try:
+                srt = ctx.csc_to_csr(m.p, m.i, m.x, m.Dim[0], m.Dim[1])
+            finally:
+                del os.environ["HS_CONVERT_SORT"], os.environ["HS_CONVERT_CHUNK"]
+            np.testing.assert_array_equal(srt[0], want.p)
+            np.testing.assert_array_equal(srt[1], want.j)
+            np.testing.assert_array_equal(srt[2], want.x)
         again = ctx.csc_to_csr(m.p.astype(np.int32), m.i, m.x, m.Dim[0], m.Dim[1])     # int32 pointers, repeat
         np.testing.assert_array_equal(again[1], want.j)
     from singlecellhaystack_b200.device import HaystackLibraryError
