@@ -181,16 +181,6 @@ __global__ void __launch_bounds__(32) k_build_slots(const int64_t* __restrict__ 
     }
 }
 
-// rows (sorted by descending length) with at least `thr` stored entries -> out[0]
-__global__ void k_count_ge(const uint32_t* __restrict__ keys_desc, int64_t n, uint32_t thr, int* __restrict__ out) {
-  int64_t lo = 0, hi = n;   // first index with key < thr
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (keys_desc[mid] >= thr) lo = mid + 1; else hi = mid;
-  }
-  out[0] = (int)lo;
-}
-
 // ---- main kernel -----------------------------------------------------------------------------------
 struct SpmmParams {
   Slots sl;

@@ -77,8 +77,9 @@ constexpr size_t kSmemB = (size_t)kStages * kBStageBytes;                       
 constexpr size_t kSmemRing = 2 * (size_t)kRingSlots * kRingSlotBytes;           // 32 KB
 constexpr size_t kSmemMma = 1024 + kSmemA + kSmemB + kSmemRing + 512;
 
-// byte offset of element (row m, cell k) inside a 128 x 64 MN-major SW128 fp16 tile (hs_umma.cu layout)
-__device__ __host__ __forceinline__ uint32_t elem_off(int m, int k) {
+// byte offset of element (row m, cell k) inside a 128 x 64 MN-major SW128 fp16 tile (hs_umma.cu layout); the kernels
+// below assemble the same offset from its row and cell parts
+[[maybe_unused]] __device__ __host__ __forceinline__ uint32_t elem_off(int m, int k) {
   const int mg = m >> 3, mi = mg >> 3, c8 = mg & 7, kg = k >> 3, k8 = k & 7;
   return (uint32_t)(((kg * 2 + mi) << 10) + (k8 << 7) + ((c8 ^ k8) << 4) + ((m & 7) << 1));
 }
@@ -1359,7 +1360,6 @@ int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_
   HS_TRY(hs_ensure_density_tiles(ctx));
   cudaStream_t st = ctx->stream;
   const int n_tr = (int)((n_rows + kTM - 1) / kTM);
-  const int n_pairs = (n_tr + 1) / 2;
   const int n_slabs = (int)((N + kSlab - 1) / kSlab);
   const int n_chunks = (n_slabs + kChunkSlabs - 1) / kChunkSlabs;
   const int64_t n_regions = (int64_t)n_tr * n_chunks;

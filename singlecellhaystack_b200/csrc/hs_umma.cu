@@ -151,21 +151,6 @@ __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   return r;
 }
 
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
-  uint32_t r;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
-  return r;
-}
-__device__ __forceinline__ void sts_u16(uint32_t a, unsigned short v) {
-  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory");
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(kUmmaThreads, 1) k_dense_umma(const UmmaParams p) {
   constexpr bool PERM = MODE == kModePerm;
