@@ -143,6 +143,7 @@ bool hs_tile_path_enabled(const hs_ctx* ctx);
 int hs_run_tile_spmm(hs_ctx* ctx, const int64_t* ptr_dev, const int32_t* sorted_rows_dev, int64_t n_rows,
                      int64_t nnz_total, const int32_t* cols_dev, const float* vals_dev, const void* pairs_dev,
                      int col_base, double* out_dev, int out_n_perm, int64_t out_n_sel, int* flags);
+const int32_t* hs_tile_row_order(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_rows, int32_t* out_dev);
 int hs_ensure_density_tiles(hs_ctx* ctx);   // hs_umma.cu: pre-tiled fp16 hi / lo density operands
 int hs_run_perm_sorted(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, int64_t n_vals_total,
                        const float* val_dev, const int32_t* ind_dev, int n_perm, int index_base, double* out_dev,

@@ -783,7 +783,9 @@ int hs_run_slab_spmm(hs_ctx* ctx, bool perm, const int64_t* ptr_dev, int64_t n_u
       if (nnz_total < 0) return hs_fail(ctx, HS_ERR_INVALID, "row pointers must be non-decreasing");
     }
     int* tile_flag = flags + 2;
-    HS_TRY(hs_run_tile_spmm(ctx, ptr_dev, rows_out, n_rows, nnz_total, cols_dev, vals_dev, pairs_dev, col_base, out_dev,
+    // (rows_in is free once the sort has run: it takes the tile path's row order)
+    const int32_t* tile_rows = hs_tile_row_order(ctx, rows_out, n_rows, rows_in);
+    HS_TRY(hs_run_tile_spmm(ctx, ptr_dev, tile_rows, n_rows, nnz_total, cols_dev, vals_dev, pairs_dev, col_base, out_dev,
                             out_n_perm, out_n_sel, tile_flag));
     run_if = tile_flag;
     if (tile_only) {          // the caller chains its own fallback on the tile flag
@@ -1090,8 +1092,9 @@ int hs_run_perm_seeded(hs_ctx* ctx, const int64_t* gene_ptr_dev, int64_t n_sel, 
                                                            0, 32, st));
     ctx->launches += 3;
     int* tile_flag = flags + 2;
+    const int32_t* tile_rows = hs_tile_row_order(ctx, rows_out, n_rows, rows_in);
     const int rc = hs_run_perm_tiles(ctx, gene_ptr_dev, n_sel, n_vals_total, val_dev, n_perm, seed, stream_base,
-                                     unit_stream_dev, rows_out, out_dev, tile_flag);
+                                     unit_stream_dev, tile_rows, out_dev, tile_flag);
     if (rc == HS_OK) {
       if (getenv("HS_PERM_CHECK")) {      // development aid: did the draw hand the call to the gather kernel?
         int h[4] = {0, 0, 0, 0};

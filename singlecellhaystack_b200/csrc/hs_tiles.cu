@@ -1343,6 +1343,30 @@ static int launch_tile_mma(hs_ctx* ctx, const uint2* entries, const unsigned lon
   return HS_OK;
 }
 
+// Rows to tile rows.  The tile kernels take 128 consecutive rows of the list they are given as a tile row, and a tile
+// row costs the same below ~20 % fill (the MMA floor) and ~1 clk per entry more above it: with the rows simply sorted by
+// length the 128 longest rows make a tile row 2.4x as slow as the median one.  Dealing the sorted rows round robin over
+// the full tile rows gives every tile row the same cut through the length spectrum (the short tail keeps its partial
+// tile row).  A row's score does not depend on which rows share its tile.
+namespace {
+__global__ void k_stripe_rows(const int32_t* __restrict__ sorted, int64_t n_rows, int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const int64_t n_full = n_rows / kTM;
+  out[i] = i < n_full * kTM ? sorted[(i % kTM) * n_full + i / kTM] : sorted[i];
+}
+}  // namespace
+
+// out may not alias sorted; returns the list the tile path should use (sorted itself when striping is switched off)
+const int32_t* hs_tile_row_order(hs_ctx* ctx, const int32_t* sorted_rows_dev, int64_t n_rows, int32_t* out_dev) {
+  if (const char* e = getenv("HS_TILE_STRIPE"))
+    if (atoi(e) == 0) return sorted_rows_dev;
+  if (n_rows < 2 * kTM) return sorted_rows_dev;
+  k_stripe_rows<<<(unsigned)((n_rows + 255) / 256), 256, 0, ctx->stream>>>(sorted_rows_dev, n_rows, out_dev);
+  ctx->launches++;
+  return out_dev;
+}
+
 // Rows (ascending cell ids) x resident density matrix -> D_KL on the tensor cores.
 //   sorted_rows_dev: row ids by descending length (n_rows of them); entries of row r at [ptr[r], ptr[r+1]) of
 //   (cols, vals) or of `pairs`; nnz_total: entries of all rows together.
