@@ -238,7 +238,10 @@ k_tile_fill(const TileSrc src, const int32_t* __restrict__ sorted_rows, int64_t 
     return (uint32_t)(cid - base);
   };
   // pass 1: entries per slab; two batches of 32 in flight per warp
-  for (int r = warp; r < kTM; r += kFillThreads / 32) {
+  // (a tile row's rows descend in length with their position: the warps take them in snake order, or warp 0 would get
+  //  the longest row of every group of sixteen)
+  for (int it = 0; it < kTM / (kFillThreads / 32); ++it) {
+    const int r = it * (kFillThreads / 32) + ((it & 1) ? kFillThreads / 32 - 1 - warp : warp);
     const int64_t b = row_beg[r];
     const uint32_t a0 = row_a[r], a1 = row_b[r];
     for (uint32_t i0 = a0; i0 < a1; i0 += 64) {
@@ -305,7 +308,10 @@ k_tile_fill(const TileSrc src, const int32_t* __restrict__ sorted_rows, int64_t 
       out[at] = make_uint2(off, (uint32_t)__half_as_ushort(h) | ((uint32_t)__half_as_ushort(l) << 16));
     }
   };
-  for (int r = warp; r < kTM; r += kFillThreads / 32) {
+  // (a tile row's rows descend in length with their position: the warps take them in snake order, or warp 0 would get
+  //  the longest row of every group of sixteen)
+  for (int it = 0; it < kTM / (kFillThreads / 32); ++it) {
+    const int r = it * (kFillThreads / 32) + ((it & 1) ? kFillThreads / 32 - 1 - warp : warp);
     const int64_t b = row_beg[r];
     const uint32_t a0 = row_a[r], a1 = row_b[r];
     const uint32_t roff = ((uint32_t)(r >> 6) << 10) | ((uint32_t)(r & 7) << 1), c8 = (uint32_t)(r >> 3) & 7u;
