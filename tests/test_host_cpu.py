@@ -176,3 +176,38 @@ def test_package_never_imports_oracle():
         txt = f.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
         assert "oracle/" not in txt and "haystack_oracle" not in txt, f
+
+
+def test_selection_ranks_are_the_positions_the_selection_takes():
+    """selection_ranks (what the device selection hs_select_by_cv_dev is given) + a stable argsort == the host selection,
+    including tied and NaN coefficients; the heavytails guard of R/haystack_continuous.R:233-235."""
+    from singlecellhaystack_b200 import haystack as hk
+    rng = np.random.default_rng(1)
+    for m in (18, 500, 12382, 30000):
+        cv = rng.gamma(2.0, 1.0, size=m)
+        cv[rng.choice(m, m // 7, replace=False)] = cv[0]          # ties
+        if m > 100:
+            cv[rng.choice(m, 5, replace=False)] = np.nan          # order(): NA last
+        for method in ("heavytails", "uniform"):
+            s_ = min(100, m)
+            ranks = hk.selection_ranks(m, s_, method)
+            assert ranks.min() >= 1 and ranks.max() <= m and ranks.size == s_
+            np.testing.assert_array_equal(np.argsort(cv, kind="stable")[ranks - 1], hk.select_genes_to_randomize(cv, s_, method))
+    with pytest.raises(ValueError, match="at least 18"):
+        hk.selection_ranks(500, 17, "heavytails")
+    with pytest.raises(ValueError, match="uniform' or 'heavytails"):
+        hk.selection_ranks(500, 100, "other")
+
+
+def test_seeding_grid_host_path_equals_the_oracle(toy):
+    """get_grid_points(method = "seeding") on R's stream: the library's draws (hs_r_sample_int / hs_r_sample_prob_one)
+    and the host distance passes give the grid of the oracle's restatement of R/haystack_highD.R:87-129."""
+    from oracle import haystack_oracle as ho
+    from oracle import r_base
+    from singlecellhaystack_b200 import grid as gr
+    from singlecellhaystack_b200.rcompat import RRandom
+    xs, _, _ = ho.scale_coords(toy["coord"])
+    for g in (5, 40):
+        got = gr.get_grid_points(xs, "seeding", g, rng=RRandom(42))
+        want = r_base.get_grid_points(xs, r_base.RRng(42), "seeding", g)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
