@@ -73,3 +73,45 @@ def test_drop_in_function_keeps_signature_and_result_object():
         assert field in src, field
     # the random draws stay R's: grid through the reference's get_grid_points, fit through its get_log_p_D_KL_continuous
     assert "sch$get_grid_points" in src and "sch$get_log_p_D_KL_continuous" in src
+
+
+def _strip_r(src: str) -> str:
+    """R source without string literals and comments (enough of a lexer for bracket matching)."""
+    out, i, n = [], 0, len(src)
+    while i < n:
+        ch = src[i]
+        if ch == "#":
+            while i < n and src[i] != "\n":
+                i += 1
+        elif ch in "\"'":
+            q = ch
+            i += 1
+            while i < n and src[i] != q:
+                i += 2 if src[i] == "\\" else 1
+            i += 1
+        elif ch == "`":
+            i = src.index("`", i + 1) + 1
+        else:
+            out.append(ch)
+            i += 1
+    return "".join(out)
+
+
+def test_r_sources_have_balanced_brackets_and_known_calls():
+    """No R interpreter here: at least every bracket of the R sources closes in order, and every b200_* function the
+    drop-in calls is defined in the package."""
+    defined, called = set(), set()
+    for f in sorted((RSHIM / "R").glob("*.R")):
+        code = _strip_r(f.read_text())
+        stack = []
+        pairs = {")": "(", "]": "[", "}": "{"}
+        for pos, ch in enumerate(code):
+            if ch in "([{":
+                stack.append(ch)
+            elif ch in ")]}":
+                assert stack and stack[-1] == pairs[ch], f"{f.name}: unbalanced '{ch}' near ...{code[max(0, pos - 60):pos + 1]!r}"
+                stack.pop()
+        assert not stack, f"{f.name}: {len(stack)} unclosed bracket(s)"
+        defined |= set(re.findall(r"^\s*([.\w]+)\s*<-\s*function\b", code, flags=re.M))
+        called |= set(re.findall(r"(?<![\w.])(\.?b200_\w+)\s*\(", code))
+    assert called <= defined, f"called but not defined: {sorted(called - defined)}"
