@@ -5,16 +5,18 @@ TEST INFRASTRUCTURE ONLY.  This module is the parity oracle: only `tests/`,
 it.  Nothing under `singlecellhaystack_b200/` imports it, and the product path never falls back
 to it.
 
-PARITY STATUS: **unpinned against a running R**.  R is not installed in the build container nor
-on the GPU boxes, and the reference's own tests assert no numbers (every numeric expectation
-is commented out: tests/testthat/test-haystack_continuous.R:16-17,30-31;
-tests/testthat/test-haystack_sparse.R:20-21,36-37).  What IS pinned (tests/test_oracle_cpu.py):
+PARITY STATUS: **pinned** against the only numbers the reference holds.  R is not installed in the build container
+nor on the GPU boxes, and the reference's own tests assert no numbers (every numeric expectation is commented out:
+tests/testthat/test-haystack_continuous.R:16-17,30-31; tests/testthat/test-haystack_sparse.R:20-21,36-37), so the pin
+is the rendered vignette, docs/articles/a01_toy_example.html:129 and :168 (set.seed(1234); haystack(dat.tsne,
+dat.expression)): with the parts of base R that call consumes restated in oracle/r_base.c (set.seed scrambling,
+Mersenne-Twister, R_unif_index, sample.int, sample(prob=), Hartigan-Wong kmeans) and drawn in the reference's order,
+this module reproduces "best df 3 / 5", the ten printed genes in order, their D_KL to all 7 printed digits and their
+log.p to the 5 printed decimals (tests/test_r_parity_cpu.py; golden copy tests/golden/toy_r1234.npz).  Also pinned
+(tests/test_oracle_cpu.py):
   * decoding of the reference's fixture data/toy.rda (dims, means, sds, sparsity),
   * the two exact-value reference tests (tests/testthat/test-extract_row.R:8-10,18-20),
-  * the rendered vignette table docs/articles/a01_toy_example.html:168 as a +-10 % smoke bound
-    (it depends on R's RNG + Hartigan-Wong k-means, which cannot be reproduced here),
-  * the identity log.p.adj - log.p.vals = log10(500) from the same table
-    (R/haystack_continuous.R:301-302),
+  * the identity log.p.adj - log.p.vals = log10(500) from the same table (R/haystack_continuous.R:301-302),
   * dense-vs-sparse agreement and algebraic invariants of the restated formulas.
 
 Every function cites the reference lines it follows (paths relative to /root/reference).
