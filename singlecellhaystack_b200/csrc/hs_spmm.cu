@@ -1,4 +1,8 @@
 // K3 / K4-sparse: sparse-row x density-matrix contraction with shared-memory staged density slabs.
+// Since round 2 this SIMT kernel is the FALLBACK: rows with grid.points <= 128 go through the tensor-core tile path
+// (hs_tiles.cu) first, and this kernel is chained behind it on a device flag (values beyond fp16, ids not ascending), or
+// runs alone for grid.points > 128.  This file also holds the row sort, the seeded draw (pair generators and the call
+// into the tile path's forward draw), the ids-given bucketing, and the gene selection by coefficient of variation.
 //   P[row, :] = sum_i val[i] * D[col[i], :]        R/haystack_continuous.R:596 (colSums(D[ind,] * val))
 //
 // Design (DESIGN.md "K3"): the density matrix D ([N][ldD] fp32, cell-major) is streamed through shared

@@ -2,10 +2,12 @@
 
 The path shards naturally: every gene's D_KL depends only on its own row plus the
 shared density state, so there is exactly one exchange step on each side of the scoring --
-  rank 0 runs the density stage, the density matrix / Q / bandwidth are broadcast (NCCL over NVLink
-  between the contexts' own device buffers: DeviceContext.density_broadcast),
-  every rank scores a contiguous, nnz-balanced gene slice and the permuted rows of the selected
-  genes it owns, and D_KL / the randomized matrix are all-gathered.
+  the density stage is sharded over the CELLS (DeviceShard, density_mode="cells": every rank computes its cells'
+  distances and densities, three in-place NCCL all-gathers over NVLink complete the row minima, the density matrix and
+  Q on every rank -- bit-identical to the single-GPU stage; "broadcast": rank 0 computes and broadcasts),
+  every rank scores a contiguous, nnz-balanced gene slice and its share of the (gene, 25-permutation) units of the
+  randomization (dealt longest first; a row's stream does not depend on the rank count), and D_KL / the randomized
+  matrix are all-gathered.
 No collective sits inside a kernel.  Everything here is SPMD: all ranks call with the same host inputs
 (each rank only uploads its own slice) and all ranks return the same result object.
 
